@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the SemPy Poisson hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one Jacobi-PCG solve (tol 1e-8) of the 3-D Poisson problem on a
+deformed box mesh of 32^3 elements at N=7 (BASELINE config 2; 16.8 M local
+nodes per GPU), i.e. ~50 passes of the hot path (fused Ax + mask + local pAp,
+gather-scatter, fused vector updates).  ``value`` is local DOF x iterations per
+second with everything resident in HBM; ``e2e`` is the same solve called through
+the drop-in API with HOST (pinned) NumPy buffers, host<->device copies timed.
+``roofline`` describes the dominant kernel (the fused Ax), timed live with CUDA
+events inside the timed region.  ``--impl reference`` times the CPU oracle (a
+NumPy restatement of the reference's algorithm) on a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ = 8
+N_ORDER = 7
+F_SHARED = 1.0 - ((N_ORDER - 1) / (N_ORDER + 1)) ** 3
+BYTES_AX = 64.0                      # u 8 + six G 48 + w 8 per local node
+BYTES_GS = 20.0 * F_SHARED           # shared nodes: read 8 + index 4 + write 8
+BYTES_UPDATE_PCG = 56.0 + 8.0        # x,p,r,Ap,rmult reads + x,r writes (+ dinv)
+BYTES_DIR_PCG = 24.0 + 8.0           # r,p reads + p write (+ dinv)
+TOL = 1e-8
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                    pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half when idle ones leak in
+            out["sm_mhz"] = float(np.median(top))
+            out["sm_max_mhz"] = mx
+            out["power_w_max"] = max(pw) if pw else None
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def build_problem(nel, perturb=0.3):
+    """Deformed box mesh of nel^3 elements at N=7 plus the manufactured RHS of
+    the reference's poisson.py:27-40.  Returns (mesh, b_host)."""
+    from sempy_b200.mesh import box_mesh
+
+    m = box_mesh(nel, perturb=perturb, seed=0)
+    m.find_physical_coordinates(N_ORDER)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    X, Y, Z = m.get_x(), m.get_y(), m.get_z()
+    b = 3 * np.pi * np.pi * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+    b = b * m.get_mass() * m.get_jaco()
+    b = m.dssum(b)
+    b = m.apply_mask(b)
+    return m, b
+
+
+def oracle_problem(nel):
+    """Same problem for the CPU oracle (its own arrays; set-up through the
+    product's mesh class, which is input preparation, not the timed path)."""
+    from sempy_b200.derivative import reference_derivative_matrix
+
+    m, b = build_problem(nel)
+    D = np.ascontiguousarray(reference_derivative_matrix(N_ORDER))
+    geom = m.get_geom()
+    g2l, gs = m.get_global_to_local_map()
+    return dict(geom=geom, D=D, g2l=g2l, gs=gs, rmult=m.get_rmult().copy(), mask=m.mask.copy(), b=b.copy(),
+                dof=m.get_num_elems() * m.Np)
+
+
+def time_oracle(prob, iters, steps, warmup):
+    """Oracle Jacobi-PCG with a fixed iteration count per step; GDOF/s."""
+    from oracle import sem_oracle as so
+
+    geom, D = prob["geom"], prob["D"]
+    axo = lambda v: so.elliptic_ax_batched(geom, v, N_ORDER, D)
+    diag = so.gather_scatter(so.jacobi_diagonal(geom, N_ORDER, D), prob["g2l"], prob["gs"])
+    dinv = prob["mask"] / diag
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, it = so.elliptic_pcg_jacobi(axo, dinv, prob["mask"], prob["g2l"], prob["gs"], prob["rmult"], prob["b"], tol=1e-30, maxit=iters)
+        t1 = time.perf_counter()
+        assert it == iters
+        if s >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return prob["dof"] * iters * steps / total / 1e9, total / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nel, iters = 10, 5
+    prob = oracle_problem(nel)
+    val, ms = time_oracle(prob, iters, args.steps, min(args.warmup, 1))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "FP64 Jacobi-PCG Poisson throughput, N=7 (local DOF x iterations / s)",
+        "value": val, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "3D Poisson, deformed box 32^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
+                   "sample": f"{nel}^3 elements, {iters} PCG iterations per step"},
+        "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle (NumPy restatement, batched matmul Ax, BLAS threads = host default) Jacobi-PCG, "
+                                   f"{nel}^3 elements N=7, {iters} iterations x {args.steps} steps"},
+        "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+
+    from sempy_b200 import _capi
+    from sempy_b200.elliptic import elliptic_ax, elliptic_pcg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU bench: see sempy_b200.distributed (not wired into bench.py yet)")
+    torch.cuda.set_device(local_rank)
+    peak, peak_kind = measured_peaks()
+    nel = args.nel
+    t_setup = time.perf_counter()
+    mesh, b_host = build_problem(nel)
+    t_setup = time.perf_counter() - t_setup
+    dof = mesh.get_num_elems() * mesh.Np
+    ctx = mesh._context()
+    lib = ctx.lib
+
+    b_dev = torch.from_numpy(b_host).cuda()
+    # pinned host buffers for the end-to-end arm
+    b_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
+    b_pin.copy_(torch.from_numpy(b_host))
+    x_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
+    b_pin_np, x_pin_np = b_pin.numpy(), x_pin.numpy()
+
+    def solve_dev():
+        return elliptic_pcg(mesh, b_dev, tol=TOL, maxit=1000)
+
+    def solve_host():
+        return elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
+
+    # ---- device-resident arm -------------------------------------------------
+    for _ in range(args.warmup):
+        x_dev, niter = solve_dev()
+    torch.cuda.synchronize()
+    _capi.check(lib.semb_profile_enable(ctx.handle, 1))
+    _capi.check(lib.semb_profile_reset(ctx.handle))
+    launches0 = lib.semb_launch_count(ctx.handle)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    iters_total = 0
+    for _ in range(args.steps):
+        x_dev, niter = solve_dev()
+        iters_total += niter
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.semb_launch_count(ctx.handle) - launches0
+    import ctypes as C
+
+    kern = {}
+    for name, kid in (("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE), ("direction", _capi.K_DIRECTION)):
+        tot, cnt = C.c_double(0), C.c_int64(0)
+        _capi.check(lib.semb_profile_get(ctx.handle, kid, C.byref(tot), C.byref(cnt)))
+        kern[name] = (tot.value, cnt.value)
+    _capi.check(lib.semb_profile_enable(ctx.handle, 0))
+    value = dof * iters_total / (ms_total * 1e-3) / 1e9
+    ax_ms = kern["ax"][0] / max(kern["ax"][1], 1)
+    ax_gbs = BYTES_AX * dof / (ax_ms * 1e-3) / 1e9
+
+    def kernel_entry(name, bytes_per_dof):
+        tot, cnt = kern[name]
+        ms = tot / max(cnt, 1)
+        gbs = bytes_per_dof * dof / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"ms": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs, "frac": gbs / peak,
+                "share_of_step": tot / ms_total}
+
+    # ---- fused Ax + mask + gather-scatter alone (the north-star 70 % target) ----
+    from sempy_b200.elliptic import _ax
+
+    p_dev = x_dev.clone()
+    for _ in range(3):
+        w = _ax(mesh, p_dev, _capi.AX_MASK | _capi.AX_GS)
+    torch.cuda.synchronize()
+    reps = 20
+    ev0.record()
+    for _ in range(reps):
+        w = _ax(mesh, p_dev, _capi.AX_MASK | _capi.AX_GS)
+    ev1.record()
+    torch.cuda.synchronize()
+    axgs_ms = ev0.elapsed_time(ev1) / reps
+    axgs_gdofs = dof / (axgs_ms * 1e-3) / 1e9
+    axgs_gbs = (BYTES_AX + BYTES_GS) * dof / (axgs_ms * 1e-3) / 1e9
+
+    # ---- end-to-end arm: host buffers through the public API ----------------
+    for _ in range(2):
+        solve_host()
+    t0 = time.perf_counter()
+    e_iters = 0
+    for _ in range(args.steps):
+        _, it = solve_host()
+        e_iters += it
+    e_s = time.perf_counter() - t0
+    e2e_val = dof * e_iters / e_s / 1e9
+    # sanity: same answer on both arms and a solved problem
+    assert np.allclose(x_pin_np, x_dev.cpu().numpy(), rtol=0, atol=1e-12)
+
+    # ---- CPU baseline: the oracle on a bounded sample of the same workload ---
+    t_cpu0 = time.perf_counter()
+    prob = oracle_problem(10)
+    cpu_val, _ = time_oracle(prob, 5, 2, 1)
+    cpu_secs = time.perf_counter() - t_cpu0
+
+    line = {
+        "metric": "FP64 Jacobi-PCG Poisson throughput, N=7 (local DOF x iterations / s)",
+        "value": value, "unit": "GDOF/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D Poisson, deformed box {nel}^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
+                   "elements": mesh.get_num_elems(), "local_dof": dof, "unique_dof": int(mesh.global_start.size - 1),
+                   "iterations_per_step": iters_total / args.steps, "cache": "inputs larger than L2 (G alone is %.0f MB)" % (48.0 * dof / 1e6),
+                   "parallelism": "1 GPU", "setup_s": t_setup},
+        "cg_iters_per_s": iters_total / (ms_total * 1e-3),
+        "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + BYTES_GS, "achieved_gbs": axgs_gbs,
+                  "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
+        "roofline": {"bound": "hbm", "kernel": "ax8_kernel (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
+                     "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak, "traffic": None,
+                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
+        "kernels": {"ax": kernel_entry("ax", BYTES_AX), "gs": kernel_entry("gs", BYTES_GS),
+                    "update": kernel_entry("update", BYTES_UPDATE_PCG), "direction": kernel_entry("direction", BYTES_DIR_PCG)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
+                "ms_per_step": e_s / args.steps * 1e3, "api": "sempy_b200.elliptic.elliptic_pcg(mesh, b_host) -> x_host"},
+        "gpu_launches": int(launches),
+        "cpu_baseline": {"value": cpu_val, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "oracle (NumPy restatement, batched matmul Ax) Jacobi-PCG, 10^3 elements N=7, 5 iterations x 2 steps (%.0f s incl. set-up)" % cpu_secs},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

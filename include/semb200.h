@@ -1,0 +1,143 @@
+/* semb200 -- C ABI of the B200-native SemPy Poisson hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, an opaque context,
+ * int status returns (0 = ok, non-zero = error; text via semb_last_error()),
+ * no exceptions and no torch types across it.  The Python package
+ * `sempy_b200` binds it with ctypes; INTEGRATION.md shows the stub a SemPy
+ * maintainer would add.  Every entry point names the reference interface
+ * (file:line under the SemPy checkout) whose work it takes over.
+ *
+ * Conventions
+ *   - All vectors are "local" element-major FP64 arrays of length E*Np,
+ *     Np = Nq^3, node index inside an element = k*Nq^2 + j*Nq + i, i fastest
+ *     (sempy/gradient.py:12-21, sempy/mass.py:31).
+ *   - `mem` says where caller-owned vector pointers live: SEMB_HOST (the
+ *     library stages through device scratch and copies back, synchronously)
+ *     or SEMB_DEVICE (used in place, asynchronously on the context's stream).
+ *   - One context per GPU; calls on one context are serialised on its stream.
+ *     The context owns D, G, the gather-scatter and mask tables, CG work
+ *     vectors and scalars.  Set-up arrays are always HOST pointers unless a
+ *     `mem` argument says otherwise.
+ */
+#ifndef SEMB200_H
+#define SEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct semb_ctx semb_ctx;
+
+enum { SEMB_HOST = 0, SEMB_DEVICE = 1 };
+/* layout of the geometric factors handed to semb_set_geom */
+enum { SEMB_G9 = 9 /* (E,3,3,Np), mesh.get_geom() */, SEMB_G6 = 6 /* (E,6,Np): rr,rs,rt,ss,st,tt */ };
+/* flags of semb_ax */
+enum { SEMB_AX_MASK = 1 /* zero Dirichlet nodes */, SEMB_AX_GS = 2 /* then gather-scatter */ };
+/* preconditioner of semb_cg */
+enum { SEMB_PRECOND_NONE = 0, SEMB_PRECOND_JACOBI = 1 };
+/* kernels that can be timed with semb_profile_* */
+enum { SEMB_K_AX = 0, SEMB_K_GS = 1, SEMB_K_UPDATE = 2, SEMB_K_DIRECTION = 3, SEMB_K_COUNT = 4 };
+
+int semb_version(void);
+/* Text of the last error on the calling thread ("" if none). */
+const char* semb_last_error(void);
+/* Number of CUDA devices visible, or a negative status. */
+int semb_device_count(void);
+
+/* ---- context ------------------------------------------------------------
+ * The reference's plug-in seam is the duck-typed mesh object (get_num_elems,
+ * Nq, Np, get_geom, get_rmult, apply_mask, dssum; sempy/elliptic.py:10-14,31)
+ * plus the gslib handle GS(comm).setup(ids) (sempy/mesh.py:437-438).  A
+ * context holds the device-resident form of exactly that state. */
+int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq);
+int semb_destroy(semb_ctx* ctx);
+/* Run on this CUDA stream (cudaStream_t as void*); NULL = the context's own. */
+int semb_set_stream(semb_ctx* ctx, void* cuda_stream);
+int semb_synchronize(semb_ctx* ctx);
+
+/* D (Nq*Nq, row-major): reference_derivative_matrix(N), sempy/derivative.py:34.
+ * Passed in so both paths use identical bits (gradient.py:7 rebuilds it). */
+int semb_set_derivative(semb_ctx* ctx, const double* D);
+/* Geometric factors of Mesh.calc_geometric_factors / get_geom
+ * (sempy/mesh.py:304-356, 514-517).  Stored on the device as 6 components. */
+int semb_set_geom(semb_ctx* ctx, const double* G, int layout, int mem);
+/* Gather-scatter tables = Mesh.get_global_to_local_map() (sempy/mesh.py:422-423,
+ * 479-480): local indices sorted by global id and the nglobal+1 segment
+ * offsets.  Replaces gslib's GS.setup (mesh.py:437-438).  Also builds
+ * rmult = 1/multiplicity (mesh.py:440-442). */
+int semb_set_gather_scatter(semb_ctx* ctx, const int64_t* global_to_local, const int64_t* global_start,
+                            int64_t nglobal);
+/* Dirichlet nodes = Mesh.get_mask_ids() (sempy/mesh.py:482-485). */
+int semb_set_mask(semb_ctx* ctx, const int64_t* mask_ids, int64_t n_mask);
+/* Copy rmult (E*Np doubles) out; mesh.get_rmult(), sempy/mesh.py:511. */
+int semb_get_rmult(semb_ctx* ctx, double* rmult, int mem);
+
+/* ---- operators ----------------------------------------------------------
+ * ap = A_local p per element: D^T G D, no assembly (sempy/elliptic.py:9-27,
+ * gradient.py:6-23,39-56).  flags add Mesh.apply_mask (mesh.py:487-494) and
+ * Mesh.dssum (mesh.py:444-447) as elliptic_cg applies them (elliptic.py:48-54). */
+int semb_ax(semb_ctx* ctx, const double* p, double* ap, int flags, int mem);
+/* In-place direct-stiffness sum; Mesh.dssum -> gslib gs(x, gs_double, gs_add),
+ * sempy/mesh.py:444-447; spec in sempy/loopy/loopy_kernels.py:26-39. */
+int semb_gs(semb_ctx* ctx, double* x, int mem);
+/* In-place x[mask_ids] = 0; Mesh.apply_mask, sempy/mesh.py:487-494. */
+int semb_mask(semb_ctx* ctx, double* x, int mem);
+/* out = sum_i w_i x_i y_i with w = rmult (weighted=1) or 1 (weighted=0):
+ * the dots of sempy/elliptic.py:33,37,51,60. `out` is a HOST double. */
+int semb_dot(semb_ctx* ctx, const double* x, const double* y, int weighted, double* out, int mem);
+/* Unassembled diagonal of the element operator; input of
+ * the Jacobi preconditioner. */
+int semb_diag(semb_ctx* ctx, double* diag, int mem);
+
+/* Batched single-element pieces, any E_b elements of order Nq-1 with the D
+ * given: sempy/gradient.py:6-23 and :39-56.  Arrays are (E_b, Nq^3). */
+int semb_gradient(int device, int Nq, const double* D, int64_t nelem, const double* U, double* Ur, double* Us,
+                  double* Ut, int mem);
+int semb_gradient_transpose(int device, int Nq, const double* D, int64_t nelem, const double* Wr,
+                            const double* Ws, const double* Wt, double* out, int mem);
+/* (Sz (x) Sy (x) Sx) U for nelem inputs, C order; sempy/kron.py:17-43.
+ * S? are (n?, m?) row-major; U is (nelem, mz*my*mx); out (nelem, nz*ny*nx). */
+int semb_kron(int device, const double* Sz, int nz, int mz, const double* Sy, int ny, int my, const double* Sx,
+              int nx, int mx, int64_t nelem, const double* U, double* out, int mem);
+
+/* ---- solvers ------------------------------------------------------------
+ * elliptic_cg(mesh, b, tol, maxit, verbose), sempy/elliptic.py:30-73, run
+ * entirely on the device: weighted dots, pAp before the gather-scatter, stop
+ * when rdotr <= max(tol^2 |b|_w^2, tol^2), early-out rdotr < 1e-20.
+ * precond = SEMB_PRECOND_JACOBI runs the PCG of sempy/iterative.py:45-85 with
+ * Minv = mask/dssum(diag) on the same local vectors (stop on r.z).
+ * history: NULL or HOST array of 5*maxit doubles, filled per iteration with
+ * rdotr0, rdotr, alpha, beta, pAp (the values the reference prints with
+ * verbose=1, elliptic.py:63-68). */
+int semb_cg(semb_ctx* ctx, const double* b, double* x, double tol, int maxit, int precond, int mem, int* niter,
+            double* history);
+
+/* cg(A,b,...) / pcg(A,Minv,b,...) of sempy/iterative.py:4-42,45-85 for any
+ * operator: the vector updates and dots run on the device, A and Minv are
+ * callbacks that receive DEVICE pointers (n doubles in, n doubles out) and
+ * return 0 on success.  Minv = NULL selects cg. */
+typedef int (*semb_apply_fn)(void* user, const double* d_in, double* d_out, int64_t n);
+int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_apply_fn Minv, void* Minv_user,
+                    const double* b, double* x, double tol, int maxit, int mem, int* niter, double* history);
+
+/* ---- device memory helpers for callers without their own allocator ------ */
+int semb_malloc(int device, void** ptr, int64_t bytes);
+int semb_free(int device, void* ptr);
+int semb_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind /*0 h2d, 1 d2h, 2 d2d*/);
+
+/* ---- measurement --------------------------------------------------------
+ * With profiling on, every launch of the named kernels is bracketed by CUDA
+ * events on the context's stream; semb_profile_get returns the summed device
+ * time and the launch count since the last reset. */
+int semb_profile_enable(semb_ctx* ctx, int on);
+int semb_profile_reset(semb_ctx* ctx);
+int semb_profile_get(semb_ctx* ctx, int kernel, double* total_ms, int64_t* launches);
+/* Kernels launched by this context since creation (all kinds). */
+int64_t semb_launch_count(semb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMB200_H */

@@ -1,0 +1,127 @@
+"""ctypes binding of libsemb200.so (include/semb200.h).
+
+The CUDA library is the product: if it is missing or cannot be loaded this
+module raises -- there is no CPU fallback anywhere in the package.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HOST, DEVICE = 0, 1
+G9, G6 = 9, 6
+AX_MASK, AX_GS = 1, 2
+PRECOND_NONE, PRECOND_JACOBI = 0, 1
+K_AX, K_GS, K_UPDATE, K_DIRECTION = 0, 1, 2, 3
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsemb200.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/semb200.h declares
+SIGNATURES = {
+    "semb_version": (C.c_int, []),
+    "semb_last_error": (C.c_char_p, []),
+    "semb_device_count": (C.c_int, []),
+    "semb_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int]),
+    "semb_destroy": (C.c_int, [C.c_void_p]),
+    "semb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "semb_synchronize": (C.c_int, [C.c_void_p]),
+    "semb_set_derivative": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "semb_set_geom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "semb_set_gather_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "semb_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "semb_get_rmult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_ax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "semb_gs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "semb_diag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_gradient": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]),
+    "semb_gradient_transpose": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]),
+    "semb_kron": (
+        C.c_int,
+        [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+         C.c_int64, C.c_void_p, C.c_void_p, C.c_int],
+    ),
+    "semb_cg": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "semb_cg_generic": (
+        C.c_int,
+        [C.c_int, C.c_int64, APPLY_FN, C.c_void_p, APPLY_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+         C.c_int, C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
+    "semb_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "semb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "semb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "semb_profile_reset": (C.c_int, [C.c_void_p]),
+    "semb_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "semb_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load the library once; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or sempy_b200/csrc/build.sh (needs nvcc). sempy_b200 has no CPU fallback."
+            )
+        handle = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().semb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"semb200 error {rc}: {msg}")
+
+
+def require_gpu():
+    n = lib().semb_device_count()
+    if n <= 0:
+        raise RuntimeError("sempy_b200 needs a CUDA device (B200); none is visible and there is no CPU fallback")
+    return n
+
+
+def is_torch_cuda(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+def as_f64(x):
+    """C-contiguous float64 view/copy of a numpy input."""
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def ptr(a):
+    """Raw address of a numpy array or torch tensor."""
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def current_device():
+    dev = os.environ.get("SEMB_DEVICE")
+    if dev is not None:
+        return int(dev)
+    return int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,131 @@
+// Shared declarations of libsemb200: error handling, the context, device scalars.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/semb200.h"
+
+namespace semb {
+
+void set_error(const std::string& msg);
+
+#define SEMB_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess) {                                                              \
+      ::semb::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" +       \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ")");                    \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define SEMB_CHECK(cond, msg)              \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::semb::set_error(msg);              \
+      return 2;                            \
+    }                                      \
+  } while (0)
+
+#define SEMB_TRY(expr)        \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+constexpr int kMaxNq = 16;
+constexpr int kNumSMs = 148;  // B200
+
+// D by value in the kernel parameter space (constant bank): after unrolling,
+// every D operand of a DFMA is a c[0][imm] operand and costs no register.
+struct DMat {
+  double d[kMaxNq * kMaxNq];  // row-major, leading dimension Nq
+};
+struct DMat8 {
+  double d[64];
+};
+// five private copies of D for the five phases of ax8_kernel (see line8)
+struct DMat8x {
+  double d[5][64];
+};
+
+// Device-resident scalars of one CG solve (no host round trip per iteration).
+struct CgScalars {
+  double rdotr;      // current r.r (or r.z), global
+  double rdotr_new;  // written by the update kernel, promoted by cg_finalize
+  double pAp;
+  double alpha;
+  double beta;
+  double TOL;
+  double norm_b;
+  int niter;
+  int done;
+  int maxit;
+  int pad;
+};
+
+// One class of gather-scatter segments: nseg segments of equal length len,
+// local indices stored segment-major at ids[off + s*len + c].
+struct GsClass {
+  int len;
+  int64_t nseg;
+  int64_t off;
+};
+
+struct Profile {
+  bool on = false;
+  std::vector<cudaEvent_t> start[SEMB_K_COUNT], stop[SEMB_K_COUNT];
+  size_t used[SEMB_K_COUNT] = {0, 0, 0, 0};
+  double total_ms[SEMB_K_COUNT] = {0, 0, 0, 0};
+  int64_t launches[SEMB_K_COUNT] = {0, 0, 0, 0};
+};
+
+}  // namespace semb
+
+struct semb_ctx {
+  int device = 0;
+  int64_t E = 0;
+  int Nq = 0;
+  int64_t Np = 0;
+  int64_t n = 0;  // E*Np
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+
+  semb::DMat D;
+  bool have_D = false;
+  double* G6 = nullptr;  // (E,6,Np)
+  bool have_G = false;
+
+  // gather-scatter schedule (shared segments only)
+  int32_t* gs_ids = nullptr;
+  int64_t gs_nids = 0;
+  std::vector<semb::GsClass> gs_classes;  // fixed-length classes (2,4,8,...)
+  int32_t* gs_var_start = nullptr;        // CSR offsets of the irregular rest
+  int64_t gs_var_nseg = 0;
+  int64_t gs_var_off = 0;
+  bool have_gs = false;
+  double* rmult = nullptr;
+
+  // Dirichlet mask: 1 bit per local node (1 = zeroed) + the id list
+  uint32_t* maskbits = nullptr;
+  int64_t* mask_ids = nullptr;
+  int64_t n_mask = 0;
+  bool have_mask = false;
+
+  // scratch / CG state
+  double* partials = nullptr;  // per-CTA partial sums
+  int64_t partials_cap = 0;
+  unsigned int* ticket = nullptr;  // last-CTA-done counters
+  semb::CgScalars* scal = nullptr;
+  double* hist = nullptr;
+  int64_t hist_cap = 0;
+  double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,stage
+  int* h_pinned = nullptr;  // pinned {done, niter}
+
+  semb::Profile prof;
+  int64_t launch_count = 0;
+};

@@ -1,0 +1,848 @@
+// libsemb200: C ABI (include/semb200.h) over the sm_100a kernels.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <utility>
+
+#include "ax_kernels.cuh"
+#include "common.cuh"
+#include "vec_kernels.cuh"
+
+namespace semb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+static inline int vec_grid(int64_t n) {
+  int64_t g = (n + VEC_NT - 1) / VEC_NT;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Brackets a launch with CUDA events when profiling is on.
+struct ProfScope {
+  semb_ctx* c;
+  int kind;
+  cudaEvent_t stop = nullptr;
+  ProfScope(semb_ctx* ctx, int k) : c(ctx), kind(k) {
+    if (!c->prof.on) return;
+    Profile& p = c->prof;
+    if (p.used[kind] == p.start[kind].size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      p.start[kind].push_back(a);
+      p.stop[kind].push_back(b);
+    }
+    cudaEventRecord(p.start[kind][p.used[kind]], c->stream);
+    stop = p.stop[kind][p.used[kind]];
+    p.used[kind]++;
+    p.launches[kind]++;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
+
+static int ensure_vec(semb_ctx* c, int which) {
+  if (c->vec[which] == nullptr) SEMB_CUDA(cudaMalloc(&c->vec[which], sizeof(double) * (size_t)std::max<int64_t>(c->n, 1)));
+  return 0;
+}
+
+static int bind_device(semb_ctx* c) {
+  SEMB_CUDA(cudaSetDevice(c->device));
+  return 0;
+}
+
+// ---- K1 dispatch -----------------------------------------------------------
+template <int NQ>
+static int launch_ax_generic(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
+                             const int* done) {
+  const unsigned grid = (unsigned)(e1 - e0);
+  const uint32_t* mb = c->maskbits;
+#define SEMB_LAUNCH_G(M, DT) \
+  ax_generic_kernel<NQ, M, DT><<<grid, NQ * NQ, 0, c->stream>>>(p, c->G6, ap, mb, c->partials, e0, e1, c->D, done)
+  if (mask && dot) SEMB_LAUNCH_G(true, true);
+  else if (mask) SEMB_LAUNCH_G(true, false);
+  else if (dot) SEMB_LAUNCH_G(false, true);
+  else SEMB_LAUNCH_G(false, false);
+#undef SEMB_LAUNCH_G
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Number of per-CTA dot partials the Ax launch over [e0,e1) writes.
+static int64_t ax_num_partials(const semb_ctx* c, int64_t e0, int64_t e1) {
+  if (c->Nq == 8) return (e1 - e0 + AX8_WARPS - 1) / AX8_WARPS;
+  return e1 - e0;
+}
+
+static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
+                     const int* done) {
+  if (e1 <= e0) return 0;
+  ProfScope ps(c, SEMB_K_AX);
+  c->launch_count++;
+  if (c->Nq == 8) {
+    static bool attr_done[64] = {false};
+    DMat8x d8;
+    for (int q = 0; q < 5; ++q) std::memcpy(d8.d[q], c->D.d, sizeof(d8.d[q]));
+    const unsigned grid = (unsigned)((e1 - e0 + AX8_WARPS - 1) / AX8_WARPS);
+    const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(c->maskbits);
+    if (!attr_done[c->device & 63]) {
+#define SEMB_ATTR(M, DT)                                                                                     \
+  SEMB_CUDA(cudaFuncSetAttribute(ax8_kernel<M, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX8_SMEM)); \
+  SEMB_CUDA(cudaFuncSetAttribute(ax8_kernel<M, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      SEMB_ATTR(true, true) SEMB_ATTR(true, false) SEMB_ATTR(false, true) SEMB_ATTR(false, false)
+#undef SEMB_ATTR
+      attr_done[c->device & 63] = true;
+    }
+#define SEMB_LAUNCH_8(M, DT) \
+  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials, e0, e1, d8, done)
+    if (mask && dot) SEMB_LAUNCH_8(true, true);
+    else if (mask) SEMB_LAUNCH_8(true, false);
+    else if (dot) SEMB_LAUNCH_8(false, true);
+    else SEMB_LAUNCH_8(false, false);
+#undef SEMB_LAUNCH_8
+    SEMB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  switch (c->Nq) {
+#define SEMB_CASE(Q) \
+  case Q:            \
+    return launch_ax_generic<Q>(c, p, ap, mask, dot, e0, e1, done);
+    SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(9) SEMB_CASE(10)
+    SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
+#undef SEMB_CASE
+    default:
+      set_error("semb_ax: unsupported Nq " + std::to_string(c->Nq));
+      return 2;
+  }
+}
+
+// ---- K2 dispatch -----------------------------------------------------------
+static int launch_gs(semb_ctx* c, double* x, const int* done) {
+  ProfScope ps(c, SEMB_K_GS);
+  for (const GsClass& k : c->gs_classes) {
+    if (k.nseg == 0) continue;
+    const int grid = vec_grid(k.nseg);
+    const int32_t* ids = c->gs_ids + k.off;
+    c->launch_count++;
+    if (k.len == 2) gs_fixed_kernel<2><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
+    else if (k.len == 4) gs_fixed_kernel<4><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
+    else if (k.len == 8) gs_fixed_kernel<8><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
+    SEMB_CUDA(cudaGetLastError());
+  }
+  if (c->gs_var_nseg > 0) {
+    c->launch_count++;
+    gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
+                                                                      c->gs_var_nseg, done);
+    SEMB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int reduce_partials(semb_ctx* c, int64_t n, int64_t stride, int nout, double* out, const int* done) {
+  c->launch_count++;
+  reduce_partials_kernel<<<1, VEC_NT, 0, c->stream>>>(c->partials, n, stride, nout, out, done);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_partials(semb_ctx* c) {
+  const int64_t need = std::max<int64_t>(c->E, 2 * (int64_t)kNumSMs * 8) + 16;
+  if (c->partials_cap < need) {
+    if (c->partials) cudaFree(c->partials);
+    SEMB_CUDA(cudaMalloc(&c->partials, sizeof(double) * (size_t)need));
+    c->partials_cap = need;
+  }
+  return 0;
+}
+
+// Host <-> device staging of caller vectors.
+struct Staged {
+  double* dev = nullptr;
+  bool owned = false;
+  ~Staged() {
+    if (owned && dev) cudaFree(dev);
+  }
+};
+static int stage_in(semb_ctx* c, const double* src, int mem, int64_t n, Staged& s, bool copy) {
+  if (mem == SEMB_DEVICE) {
+    s.dev = const_cast<double*>(src);
+    return 0;
+  }
+  SEMB_CUDA(cudaMalloc(&s.dev, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+  s.owned = true;
+  if (copy) SEMB_CUDA(cudaMemcpyAsync(s.dev, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
+  if (mem == SEMB_DEVICE) return 0;
+  SEMB_CUDA(cudaMemcpyAsync(dst, s.dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int build_jacobi(semb_ctx* c) {
+  SEMB_TRY(ensure_vec(c, 4));
+  double* d = c->vec[4];
+  c->launch_count++;
+  diag_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->G6, d, c->E, c->Nq, c->D);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_TRY(launch_gs(c, d, nullptr));
+  c->launch_count++;
+  jacobi_invert_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(d, c->have_mask ? c->maskbits : nullptr, c->n);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace semb
+
+using namespace semb;
+
+extern "C" {
+
+int semb_version(void) { return 100; }
+const char* semb_last_error(void) { return g_last_error.c_str(); }
+
+int semb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq) {
+  SEMB_CHECK(out != nullptr, "semb_create: out is NULL");
+  SEMB_CHECK(num_elems > 0, "semb_create: num_elems must be positive");
+  SEMB_CHECK(Nq >= 2 && Nq <= kMaxNq, "semb_create: Nq must be in [2,16]");
+  SEMB_CHECK((int64_t)num_elems * Nq * Nq * Nq < (int64_t)2147483647, "semb_create: more than 2^31 local nodes per GPU");
+  SEMB_CUDA(cudaSetDevice(device));
+  semb_ctx* c = new semb_ctx();
+  c->device = device;
+  c->E = num_elems;
+  c->Nq = Nq;
+  c->Np = (int64_t)Nq * Nq * Nq;
+  c->n = c->E * c->Np;
+  SEMB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  SEMB_CUDA(cudaMalloc(&c->scal, sizeof(CgScalars) + 8 * sizeof(double)));
+  SEMB_CUDA(cudaMemset(c->scal, 0, sizeof(CgScalars) + 8 * sizeof(double)));
+  SEMB_CUDA(cudaMallocHost(&c->h_pinned, 64));
+  if (ensure_partials(c)) return 1;
+  *out = c;
+  return 0;
+}
+
+int semb_destroy(semb_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->G6);
+  cudaFree(c->gs_ids);
+  cudaFree(c->gs_var_start);
+  cudaFree(c->rmult);
+  cudaFree(c->maskbits);
+  cudaFree(c->mask_ids);
+  cudaFree(c->partials);
+  cudaFree(c->scal);
+  cudaFree(c->hist);
+  for (double* v : c->vec) cudaFree(v);
+  cudaFreeHost(c->h_pinned);
+  for (int k = 0; k < SEMB_K_COUNT; ++k) {
+    for (cudaEvent_t e : c->prof.start[k]) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prof.stop[k]) cudaEventDestroy(e);
+  }
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+int semb_set_stream(semb_ctx* c, void* s) {
+  SEMB_CHECK(c != nullptr, "semb_set_stream: ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return 0;
+}
+
+int semb_synchronize(semb_ctx* c) {
+  SEMB_CHECK(c != nullptr, "semb_synchronize: ctx is NULL");
+  SEMB_TRY(bind_device(c));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_set_derivative(semb_ctx* c, const double* D) {
+  SEMB_CHECK(c && D, "semb_set_derivative: NULL argument");
+  std::memset(c->D.d, 0, sizeof(c->D.d));
+  std::memcpy(c->D.d, D, sizeof(double) * c->Nq * c->Nq);
+  c->have_D = true;
+  return 0;
+}
+
+// (E,3,3,Np) -> (E,6,Np) on the device
+__global__ void g9_to_g6_kernel(const double* __restrict__ g9, double* __restrict__ g6, int64_t E, int64_t Np) {
+  const int64_t n = E * 6 * Np;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = q / (6 * Np);
+    const int c = (int)((q / Np) % 6);
+    const int64_t node = q % Np;
+    const int src = c == 0 ? 0 : c == 1 ? 1 : c == 2 ? 2 : c == 3 ? 4 : c == 4 ? 5 : 8;
+    g6[q] = g9[(e * 9 + src) * Np + node];
+  }
+}
+
+int semb_set_geom(semb_ctx* c, const double* G, int layout, int mem) {
+  SEMB_CHECK(c && G, "semb_set_geom: NULL argument");
+  SEMB_CHECK(layout == SEMB_G9 || layout == SEMB_G6, "semb_set_geom: layout must be SEMB_G9 or SEMB_G6");
+  SEMB_TRY(bind_device(c));
+  const size_t bytes6 = sizeof(double) * 6 * (size_t)c->n;
+  if (!c->G6) SEMB_CUDA(cudaMalloc(&c->G6, bytes6));
+  if (layout == SEMB_G6) {
+    SEMB_CUDA(cudaMemcpyAsync(c->G6, G, bytes6, mem == SEMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              c->stream));
+  } else {
+    // stream the 9-component array through a bounded device buffer, element chunks at a time
+    const int64_t chunkE = std::max<int64_t>(1, std::min<int64_t>(c->E, (int64_t)(256u << 20) / (9 * 8 * c->Np)));
+    double* tmp = nullptr;
+    if (mem == SEMB_HOST) SEMB_CUDA(cudaMalloc(&tmp, sizeof(double) * 9 * (size_t)(chunkE * c->Np)));
+    for (int64_t e0 = 0; e0 < c->E; e0 += chunkE) {
+      const int64_t ne = std::min(chunkE, c->E - e0);
+      const double* src = G + e0 * 9 * c->Np;
+      if (mem == SEMB_HOST) {
+        SEMB_CUDA(cudaMemcpyAsync(tmp, src, sizeof(double) * 9 * (size_t)(ne * c->Np), cudaMemcpyHostToDevice, c->stream));
+        src = tmp;
+      }
+      g9_to_g6_kernel<<<vec_grid(ne * 6 * c->Np), VEC_NT, 0, c->stream>>>(src, c->G6 + e0 * 6 * c->Np, ne, c->Np);
+      SEMB_CUDA(cudaGetLastError());
+    }
+    SEMB_CUDA(cudaStreamSynchronize(c->stream));
+    if (tmp) cudaFree(tmp);
+  }
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_G = true;
+  return 0;
+}
+
+int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gstart, int64_t nglobal) {
+  SEMB_CHECK(c && g2l && gstart, "semb_set_gather_scatter: NULL argument");
+  SEMB_CHECK(nglobal > 0 && gstart[0] == 0 && gstart[nglobal] == c->n,
+             "semb_set_gather_scatter: global_start must run from 0 to E*Np");
+  SEMB_TRY(bind_device(c));
+  // Classify the segments with more than one local copy by length.
+  std::vector<std::pair<int32_t, int64_t>> cls[4];  // len 2, 4, 8, other : (first local id, segment)
+  for (int64_t s = 0; s < nglobal; ++s) {
+    const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
+    SEMB_CHECK(len >= 1, "semb_set_gather_scatter: empty segment");
+    if (len == 1) continue;
+    int64_t first = g2l[lo];
+    for (int64_t q = lo + 1; q < lo + len; ++q) first = std::min(first, g2l[q]);
+    SEMB_CHECK(first >= 0 && first < c->n, "semb_set_gather_scatter: local index out of range");
+    const int k = len == 2 ? 0 : len == 4 ? 1 : len == 8 ? 2 : 3;
+    cls[k].emplace_back((int32_t)first, s);
+  }
+  // Order segments by their first local index: neighbouring threads then touch neighbouring memory.
+  for (auto& v : cls) std::sort(v.begin(), v.end());
+  std::vector<int32_t> ids;
+  std::vector<int32_t> var_start;
+  c->gs_classes.clear();
+  const int lens[3] = {2, 4, 8};
+  auto emit = [&](int64_t s) {
+    const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
+    const size_t at = ids.size();
+    for (int64_t q = lo; q < lo + len; ++q) ids.push_back((int32_t)g2l[q]);
+    std::sort(ids.begin() + at, ids.end());  // fixed summation order: ascending local index
+  };
+  for (int k = 0; k < 3; ++k) {
+    while (ids.size() % 4) ids.push_back(0);
+    GsClass gc{lens[k], (int64_t)cls[k].size(), (int64_t)ids.size()};
+    for (auto& pr : cls[k]) emit(pr.second);
+    c->gs_classes.push_back(gc);
+  }
+  while (ids.size() % 4) ids.push_back(0);
+  c->gs_var_off = (int64_t)ids.size();
+  c->gs_var_nseg = (int64_t)cls[3].size();
+  var_start.push_back(0);
+  for (auto& pr : cls[3]) {
+    emit(pr.second);
+    var_start.push_back((int32_t)(ids.size() - c->gs_var_off));
+  }
+  c->gs_nids = (int64_t)ids.size();
+  cudaFree(c->gs_ids);
+  cudaFree(c->gs_var_start);
+  c->gs_ids = nullptr;
+  c->gs_var_start = nullptr;
+  SEMB_CUDA(cudaMalloc(&c->gs_ids, sizeof(int32_t) * std::max<size_t>(ids.size(), 4)));
+  SEMB_CUDA(cudaMemcpy(c->gs_ids, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
+  SEMB_CUDA(cudaMalloc(&c->gs_var_start, sizeof(int32_t) * var_start.size()));
+  SEMB_CUDA(cudaMemcpy(c->gs_var_start, var_start.data(), sizeof(int32_t) * var_start.size(), cudaMemcpyHostToDevice));
+  c->have_gs = true;
+  // rmult = 1 / gs(ones)   (sempy/mesh.py:440-442)
+  if (!c->rmult) SEMB_CUDA(cudaMalloc(&c->rmult, sizeof(double) * (size_t)c->n));
+  fill_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, 1.0, c->n);
+  SEMB_TRY(launch_gs(c, c->rmult, nullptr));
+  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->n);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->vec[4]) {  // cached Jacobi diagonal is stale
+    cudaFree(c->vec[4]);
+    c->vec[4] = nullptr;
+  }
+  return 0;
+}
+
+int semb_set_mask(semb_ctx* c, const int64_t* mask_ids, int64_t n_mask) {
+  SEMB_CHECK(c && (mask_ids || n_mask == 0) && n_mask >= 0, "semb_set_mask: bad argument");
+  SEMB_TRY(bind_device(c));
+  const size_t words = ((size_t)c->n + 63) / 64 * 2;
+  std::vector<uint32_t> bits(words, 0u);
+  for (int64_t q = 0; q < n_mask; ++q) {
+    const int64_t id = mask_ids[q];
+    SEMB_CHECK(id >= 0 && id < c->n, "semb_set_mask: id out of range");
+    bits[id >> 5] |= 1u << (id & 31);
+  }
+  cudaFree(c->maskbits);
+  cudaFree(c->mask_ids);
+  c->maskbits = nullptr;
+  c->mask_ids = nullptr;
+  SEMB_CUDA(cudaMalloc(&c->maskbits, sizeof(uint32_t) * words));
+  SEMB_CUDA(cudaMemcpy(c->maskbits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
+  SEMB_CUDA(cudaMalloc(&c->mask_ids, sizeof(int64_t) * std::max<int64_t>(n_mask, 1)));
+  if (n_mask) SEMB_CUDA(cudaMemcpy(c->mask_ids, mask_ids, sizeof(int64_t) * n_mask, cudaMemcpyHostToDevice));
+  c->n_mask = n_mask;
+  c->have_mask = true;
+  if (c->vec[4]) {
+    cudaFree(c->vec[4]);
+    c->vec[4] = nullptr;
+  }
+  return 0;
+}
+
+int semb_get_rmult(semb_ctx* c, double* rmult, int mem) {
+  SEMB_CHECK(c && rmult, "semb_get_rmult: NULL argument");
+  SEMB_CHECK(c->have_gs, "semb_get_rmult: call semb_set_gather_scatter first");
+  SEMB_TRY(bind_device(c));
+  SEMB_CUDA(cudaMemcpyAsync(rmult, c->rmult, sizeof(double) * (size_t)c->n,
+                            mem == SEMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_ax(semb_ctx* c, const double* p, double* ap, int flags, int mem) {
+  SEMB_CHECK(c && p && ap, "semb_ax: NULL argument");
+  SEMB_CHECK(c->have_D && c->have_G, "semb_ax: derivative matrix and geometric factors must be set first");
+  const bool mask = flags & SEMB_AX_MASK, gs = flags & SEMB_AX_GS;
+  SEMB_CHECK(!mask || c->have_mask, "semb_ax: SEMB_AX_MASK without semb_set_mask");
+  SEMB_CHECK(!gs || c->have_gs, "semb_ax: SEMB_AX_GS without semb_set_gather_scatter");
+  SEMB_CHECK(mem == SEMB_HOST || p != ap, "semb_ax: in-place application is not supported");
+  SEMB_TRY(bind_device(c));
+  Staged in, out;
+  SEMB_TRY(stage_in(c, p, mem, c->n, in, true));
+  SEMB_TRY(stage_in(c, ap, mem, c->n, out, false));
+  SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, c->E, nullptr));
+  if (gs) SEMB_TRY(launch_gs(c, out.dev, nullptr));
+  SEMB_TRY(stage_out(c, ap, mem, c->n, out));
+  return 0;
+}
+
+int semb_gs(semb_ctx* c, double* x, int mem) {
+  SEMB_CHECK(c && x, "semb_gs: NULL argument");
+  SEMB_CHECK(c->have_gs, "semb_gs: call semb_set_gather_scatter first");
+  SEMB_TRY(bind_device(c));
+  Staged v;
+  SEMB_TRY(stage_in(c, x, mem, c->n, v, true));
+  SEMB_TRY(launch_gs(c, v.dev, nullptr));
+  SEMB_TRY(stage_out(c, x, mem, c->n, v));
+  return 0;
+}
+
+int semb_mask(semb_ctx* c, double* x, int mem) {
+  SEMB_CHECK(c && x, "semb_mask: NULL argument");
+  SEMB_CHECK(c->have_mask, "semb_mask: call semb_set_mask first");
+  SEMB_TRY(bind_device(c));
+  Staged v;
+  SEMB_TRY(stage_in(c, x, mem, c->n, v, true));
+  if (c->n_mask > 0) {
+    c->launch_count++;
+    mask_kernel<<<vec_grid(c->n_mask), VEC_NT, 0, c->stream>>>(v.dev, c->mask_ids, c->n_mask);
+    SEMB_CUDA(cudaGetLastError());
+  }
+  SEMB_TRY(stage_out(c, x, mem, c->n, v));
+  return 0;
+}
+
+int semb_dot(semb_ctx* c, const double* x, const double* y, int weighted, double* out, int mem) {
+  SEMB_CHECK(c && x && y && out, "semb_dot: NULL argument");
+  SEMB_CHECK(!weighted || c->have_gs, "semb_dot: weighted dot needs semb_set_gather_scatter");
+  SEMB_TRY(bind_device(c));
+  Staged a, b;
+  SEMB_TRY(stage_in(c, x, mem, c->n, a, true));
+  SEMB_TRY(stage_in(c, y, mem, c->n, b, true));
+  const int grid = vec_grid(c->n);
+  c->launch_count++;
+  if (weighted) dot_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(a.dev, b.dev, c->rmult, c->n, c->partials);
+  else dot_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(a.dev, b.dev, nullptr, c->n, c->partials);
+  SEMB_CUDA(cudaGetLastError());
+  double* scratch = reinterpret_cast<double*>(c->scal + 1);
+  SEMB_TRY(reduce_partials(c, grid, 0, 1, scratch, nullptr));
+  SEMB_CUDA(cudaMemcpyAsync(out, scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_diag(semb_ctx* c, double* diag, int mem) {
+  SEMB_CHECK(c && diag, "semb_diag: NULL argument");
+  SEMB_CHECK(c->have_D && c->have_G, "semb_diag: derivative matrix and geometric factors must be set first");
+  SEMB_TRY(bind_device(c));
+  Staged v;
+  SEMB_TRY(stage_in(c, diag, mem, c->n, v, false));
+  c->launch_count++;
+  diag_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->G6, v.dev, c->E, c->Nq, c->D);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_TRY(stage_out(c, diag, mem, c->n, v));
+  return 0;
+}
+
+// ---- batched single-element pieces ------------------------------------------
+static int make_dmat(DMat& dm, const double* D, int Nq) {
+  SEMB_CHECK(D != nullptr && Nq >= 1 && Nq <= kMaxNq, "D is NULL or Nq outside [1,16]");
+  std::memset(dm.d, 0, sizeof(dm.d));
+  std::memcpy(dm.d, D, sizeof(double) * Nq * Nq);
+  return 0;
+}
+
+struct TmpBuf {
+  double* dev = nullptr;
+  bool owned = false;
+  ~TmpBuf() {
+    if (owned && dev) cudaFree(dev);
+  }
+  int in(const double* src, int mem, size_t count, bool copy) {
+    if (mem == SEMB_DEVICE) {
+      dev = const_cast<double*>(src);
+      return 0;
+    }
+    SEMB_CUDA(cudaMalloc(&dev, sizeof(double) * std::max<size_t>(count, 1)));
+    owned = true;
+    if (copy) SEMB_CUDA(cudaMemcpy(dev, src, sizeof(double) * count, cudaMemcpyHostToDevice));
+    return 0;
+  }
+  int out(double* dst, int mem, size_t count) {
+    if (mem == SEMB_DEVICE) return 0;
+    SEMB_CUDA(cudaMemcpy(dst, dev, sizeof(double) * count, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+};
+
+int semb_gradient(int device, int Nq, const double* D, int64_t nelem, const double* U, double* Ur, double* Us,
+                  double* Ut, int mem) {
+  SEMB_CHECK(U && Ur && Us && Ut && nelem > 0, "semb_gradient: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  DMat dm;
+  SEMB_TRY(make_dmat(dm, D, Nq));
+  const size_t cnt = (size_t)nelem * Nq * Nq * Nq;
+  TmpBuf u, r, s, t;
+  SEMB_TRY(u.in(U, mem, cnt, true));
+  SEMB_TRY(r.in(Ur, mem, cnt, false));
+  SEMB_TRY(s.in(Us, mem, cnt, false));
+  SEMB_TRY(t.in(Ut, mem, cnt, false));
+  const int Np = Nq * Nq * Nq;
+  const int nt = std::min(256, ((Np + 31) / 32) * 32);
+  const size_t smem = sizeof(double) * 3 * Np;
+  SEMB_CUDA(cudaFuncSetAttribute(gradient_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 4096)));
+  gradient_kernel<false><<<(unsigned)nelem, nt, smem>>>(u.dev, nullptr, nullptr, r.dev, s.dev, t.dev, Nq, dm);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaDeviceSynchronize());
+  SEMB_TRY(r.out(Ur, mem, cnt));
+  SEMB_TRY(s.out(Us, mem, cnt));
+  SEMB_TRY(t.out(Ut, mem, cnt));
+  return 0;
+}
+
+int semb_gradient_transpose(int device, int Nq, const double* D, int64_t nelem, const double* Wr, const double* Ws,
+                            const double* Wt, double* out, int mem) {
+  SEMB_CHECK(Wr && Ws && Wt && out && nelem > 0, "semb_gradient_transpose: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  DMat dm;
+  SEMB_TRY(make_dmat(dm, D, Nq));
+  const size_t cnt = (size_t)nelem * Nq * Nq * Nq;
+  TmpBuf a, b, cc, o;
+  SEMB_TRY(a.in(Wr, mem, cnt, true));
+  SEMB_TRY(b.in(Ws, mem, cnt, true));
+  SEMB_TRY(cc.in(Wt, mem, cnt, true));
+  SEMB_TRY(o.in(out, mem, cnt, false));
+  const int Np = Nq * Nq * Nq;
+  const int nt = std::min(256, ((Np + 31) / 32) * 32);
+  const size_t smem = sizeof(double) * 3 * Np;
+  SEMB_CUDA(cudaFuncSetAttribute(gradient_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 4096)));
+  gradient_kernel<true><<<(unsigned)nelem, nt, smem>>>(a.dev, b.dev, cc.dev, o.dev, nullptr, nullptr, Nq, dm);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaDeviceSynchronize());
+  SEMB_TRY(o.out(out, mem, cnt));
+  return 0;
+}
+
+int semb_kron(int device, const double* Sz, int nz, int mz, const double* Sy, int ny, int my, const double* Sx, int nx,
+              int mx, int64_t nelem, const double* U, double* out, int mem) {
+  SEMB_CHECK(Sz && Sy && Sx && U && out && nelem > 0, "semb_kron: bad argument");
+  SEMB_CHECK(nz > 0 && ny > 0 && nx > 0 && mz > 0 && my > 0 && mx > 0, "semb_kron: non-positive dimension");
+  const size_t smem = sizeof(double) * ((size_t)mz * my * mx + (size_t)mz * my * nx + (size_t)mz * ny * nx);
+  SEMB_CHECK(smem <= 200 * 1024, "semb_kron: factors too large for one CTA's shared memory");
+  SEMB_CUDA(cudaSetDevice(device));
+  const size_t nin = (size_t)mz * my * mx, nout = (size_t)nz * ny * nx;
+  TmpBuf sz, sy, sx, u, o;
+  // the factors are always HOST arrays (tiny)
+  SEMB_TRY(sz.in(Sz, SEMB_HOST, (size_t)nz * mz, true));
+  SEMB_TRY(sy.in(Sy, SEMB_HOST, (size_t)ny * my, true));
+  SEMB_TRY(sx.in(Sx, SEMB_HOST, (size_t)nx * mx, true));
+  SEMB_TRY(u.in(U, mem, (size_t)nelem * nin, true));
+  SEMB_TRY(o.in(out, mem, (size_t)nelem * nout, false));
+  SEMB_CUDA(cudaFuncSetAttribute(kron_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  kron_kernel<<<(unsigned)nelem, 256, smem>>>(sz.dev, nz, mz, sy.dev, ny, my, sx.dev, nx, mx, u.dev, o.dev);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaDeviceSynchronize());
+  SEMB_TRY(o.out(out, mem, (size_t)nelem * nout));
+  return 0;
+}
+
+// ---- solvers ---------------------------------------------------------------
+int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int precond, int mem, int* niter,
+            double* history) {
+  SEMB_CHECK(c && b && x && niter, "semb_cg: NULL argument");
+  SEMB_CHECK(c->have_D && c->have_G && c->have_gs, "semb_cg: derivative, geometric factors and gather-scatter must be set");
+  SEMB_CHECK(precond == SEMB_PRECOND_NONE || precond == SEMB_PRECOND_JACOBI, "semb_cg: unknown preconditioner");
+  SEMB_CHECK(maxit >= 0, "semb_cg: maxit must be non-negative");
+  SEMB_TRY(bind_device(c));
+  const bool jac = precond == SEMB_PRECOND_JACOBI;
+  const int64_t n = c->n;
+  for (int v = 0; v < 3; ++v) SEMB_TRY(ensure_vec(c, v));
+  double *r = c->vec[0], *p = c->vec[1], *Ap = c->vec[2];
+  const double* bdev = b;
+  double* xdev = x;
+  if (mem == SEMB_HOST) {
+    SEMB_TRY(ensure_vec(c, 3));
+    SEMB_TRY(ensure_vec(c, 5));
+    SEMB_CUDA(cudaMemcpyAsync(c->vec[5], b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    bdev = c->vec[5];
+    xdev = c->vec[3];
+  }
+  if (jac && c->vec[4] == nullptr) SEMB_TRY(build_jacobi(c));
+  const double* dinv = c->vec[4];
+  if (history != nullptr && maxit > 0) {
+    if (c->hist_cap < 5 * (int64_t)maxit) {
+      cudaFree(c->hist);
+      c->hist = nullptr;
+      SEMB_CUDA(cudaMalloc(&c->hist, sizeof(double) * 5 * (size_t)maxit));
+      c->hist_cap = 5 * (int64_t)maxit;
+    }
+  }
+  double* hist = (history != nullptr && maxit > 0) ? c->hist : nullptr;
+  CgScalars* s = c->scal;
+  double* two = reinterpret_cast<double*>(c->scal + 1);
+  const int grid = vec_grid(n);
+  const bool mask = c->have_mask;
+
+  c->launch_count += 2;
+  if (jac) cg_init_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(bdev, xdev, r, p, c->rmult, dinv, n, c->partials);
+  else cg_init_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(bdev, xdev, r, p, c->rmult, nullptr, n, c->partials);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_TRY(reduce_partials(c, grid, grid, jac ? 2 : 1, two, nullptr));
+  cg_init_scalars_kernel<<<1, 1, 0, c->stream>>>(s, two, tol, maxit, jac ? 1 : 0);
+  SEMB_CUDA(cudaGetLastError());
+
+  const int* done = &s->done;
+  int issued = 0;
+  int chunk = 1;
+  while (true) {
+    SEMB_CUDA(cudaMemcpyAsync(c->h_pinned, &s->niter, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SEMB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[1] || issued >= maxit) break;
+    const int todo = std::min(chunk, maxit - issued);
+    for (int it = 0; it < todo; ++it) {
+      // Ap = mask(A p), local pAp partials      (elliptic.py:48-51)
+      SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
+      SEMB_TRY(reduce_partials(c, ax_num_partials(c, 0, c->E), 0, 1, &s->pAp, done));
+      // Ap = dssum(Ap)                          (elliptic.py:54)
+      SEMB_TRY(launch_gs(c, Ap, done));
+      // x, r, rdotr                             (elliptic.py:56-60)
+      {
+        ProfScope ps(c, SEMB_K_UPDATE);
+        c->launch_count++;
+        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->rmult, dinv, s, n, c->partials);
+        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->rmult, nullptr, s, n, c->partials);
+        SEMB_CUDA(cudaGetLastError());
+      }
+      SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
+      c->launch_count++;
+      cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
+      SEMB_CUDA(cudaGetLastError());
+      // p = z + beta p                          (elliptic.py:70)
+      {
+        ProfScope ps(c, SEMB_K_DIRECTION);
+        c->launch_count++;
+        if (jac) cg_direction_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(p, r, dinv, s, n);
+        else cg_direction_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(p, r, nullptr, s, n);
+        SEMB_CUDA(cudaGetLastError());
+      }
+    }
+    issued += todo;
+    chunk = std::min(chunk * 2, 16);
+  }
+  *niter = c->h_pinned[0];
+  if (history != nullptr && *niter > 0)
+    SEMB_CUDA(cudaMemcpyAsync(history, c->hist, sizeof(double) * 5 * (size_t)(*niter), cudaMemcpyDeviceToHost, c->stream));
+  if (mem == SEMB_HOST)
+    SEMB_CUDA(cudaMemcpyAsync(x, xdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_apply_fn Minv, void* Minv_user,
+                    const double* b, double* x, double tol, int maxit, int mem, int* niter, double* history) {
+  SEMB_CHECK(A && b && x && niter && n > 0, "semb_cg_generic: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  const bool pre = Minv != nullptr;
+  double* buf = nullptr;  // r, p, Ap, z, xs, bs
+  SEMB_CUDA(cudaMalloc(&buf, sizeof(double) * 6 * (size_t)n));
+  struct Guard {
+    double* p;
+    double* q;
+    ~Guard() {
+      cudaFree(p);
+      cudaFree(q);
+    }
+  } guard{buf, nullptr};
+  double *r = buf, *p = buf + n, *Ap = buf + 2 * n, *z = buf + 3 * n, *xs = buf + 4 * n, *bs = buf + 5 * n;
+  const int grid = vec_grid(n);
+  double* sc = nullptr;  // partials[grid] + scalars: [0]=rdotr [1]=pAp [2]=rdotr_new [3]=norm_b
+  SEMB_CUDA(cudaMalloc(&sc, sizeof(double) * (grid + 8)));
+  guard.q = sc;
+  double* partials = sc + 8;
+  const double* bdev = b;
+  double* xdev = x;
+  if (mem == SEMB_HOST) {
+    SEMB_CUDA(cudaMemcpy(bs, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    bdev = bs;
+    xdev = xs;
+  }
+  auto dot = [&](const double* a, const double* bb, double* out_dev, double* out_host) -> int {
+    dot_kernel<false><<<grid, VEC_NT>>>(a, bb, nullptr, n, partials);
+    reduce_partials_kernel<<<1, VEC_NT>>>(partials, grid, 0, 1, out_dev, nullptr);
+    SEMB_CUDA(cudaGetLastError());
+    SEMB_CUDA(cudaMemcpy(out_host, out_dev, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  SEMB_CUDA(cudaMemset(xdev, 0, sizeof(double) * (size_t)n));
+  SEMB_CUDA(cudaMemcpy(r, bdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice));
+  double norm_b = 0.0, rdotr = 0.0, pAp = 0.0, rnew = 0.0;
+  SEMB_TRY(dot(bdev, bdev, sc + 3, &norm_b));
+  const double TOL = std::max(tol * tol * norm_b, tol * tol);
+  if (pre) {
+    SEMB_CUDA(cudaDeviceSynchronize());
+    SEMB_CHECK(Minv(Minv_user, r, z, n) == 0, "semb_cg_generic: Minv callback failed");
+    SEMB_TRY(dot(r, z, sc + 0, &rdotr));
+    SEMB_CUDA(cudaMemcpy(p, z, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice));
+  } else {
+    rdotr = norm_b;
+    SEMB_CUDA(cudaMemcpy(sc + 0, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice));
+    SEMB_CUDA(cudaMemcpy(p, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice));
+  }
+  int it = 0;
+  const bool early = !pre && rdotr < 1.0e-20;  // iterative.py:15 (cg only)
+  while (!early && it < maxit && rdotr > TOL) {
+    SEMB_CUDA(cudaDeviceSynchronize());
+    SEMB_CHECK(A(A_user, p, Ap, n) == 0, "semb_cg_generic: operator callback failed");
+    SEMB_TRY(dot(p, Ap, sc + 1, &pAp));
+    axpy_pair_kernel<<<grid, VEC_NT>>>(xdev, r, p, Ap, sc + 0, sc + 1, n);
+    SEMB_CUDA(cudaGetLastError());
+    if (pre) {
+      SEMB_CUDA(cudaDeviceSynchronize());
+      SEMB_CHECK(Minv(Minv_user, r, z, n) == 0, "semb_cg_generic: Minv callback failed");
+      SEMB_TRY(dot(r, z, sc + 2, &rnew));
+    } else {
+      SEMB_TRY(dot(r, r, sc + 2, &rnew));
+    }
+    xpby_kernel<<<grid, VEC_NT>>>(p, pre ? z : r, sc + 2, sc + 0, n);
+    SEMB_CUDA(cudaGetLastError());
+    if (history) {
+      double* h = history + 5 * (size_t)it;
+      h[0] = rdotr;
+      h[1] = rnew;
+      h[2] = rdotr / pAp;
+      h[3] = rnew / rdotr;
+      h[4] = pAp;
+    }
+    SEMB_CUDA(cudaMemcpy(sc + 0, sc + 2, sizeof(double), cudaMemcpyDeviceToDevice));
+    rdotr = rnew;
+    ++it;
+  }
+  *niter = it;
+  if (mem == SEMB_HOST) SEMB_CUDA(cudaMemcpy(x, xdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  SEMB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ---- memory helpers --------------------------------------------------------
+int semb_malloc(int device, void** ptr, int64_t bytes) {
+  SEMB_CHECK(ptr && bytes >= 0, "semb_malloc: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  SEMB_CUDA(cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return 0;
+}
+int semb_free(int device, void* ptr) {
+  SEMB_CUDA(cudaSetDevice(device));
+  SEMB_CUDA(cudaFree(ptr));
+  return 0;
+}
+int semb_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind) {
+  SEMB_CHECK(dst && src && bytes >= 0 && kind >= 0 && kind <= 2, "semb_memcpy: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  SEMB_CUDA(cudaMemcpy(dst, src, (size_t)bytes, k));
+  return 0;
+}
+
+// ---- measurement -----------------------------------------------------------
+static int prof_flush(semb_ctx* c) {
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < SEMB_K_COUNT; ++k) {
+    for (size_t q = 0; q < c->prof.used[k]; ++q) {
+      float ms = 0.f;
+      SEMB_CUDA(cudaEventElapsedTime(&ms, c->prof.start[k][q], c->prof.stop[k][q]));
+      c->prof.total_ms[k] += ms;
+    }
+    c->prof.used[k] = 0;
+  }
+  return 0;
+}
+int semb_profile_enable(semb_ctx* c, int on) {
+  SEMB_CHECK(c != nullptr, "semb_profile_enable: ctx is NULL");
+  SEMB_TRY(bind_device(c));
+  if (!on && c->prof.on) SEMB_TRY(prof_flush(c));
+  c->prof.on = on != 0;
+  return 0;
+}
+int semb_profile_reset(semb_ctx* c) {
+  SEMB_CHECK(c != nullptr, "semb_profile_reset: ctx is NULL");
+  SEMB_TRY(bind_device(c));
+  SEMB_TRY(prof_flush(c));
+  for (int k = 0; k < SEMB_K_COUNT; ++k) {
+    c->prof.total_ms[k] = 0.0;
+    c->prof.launches[k] = 0;
+  }
+  return 0;
+}
+int semb_profile_get(semb_ctx* c, int kernel, double* total_ms, int64_t* launches) {
+  SEMB_CHECK(c && total_ms && launches && kernel >= 0 && kernel < SEMB_K_COUNT, "semb_profile_get: bad argument");
+  SEMB_TRY(bind_device(c));
+  SEMB_TRY(prof_flush(c));
+  *total_ms = c->prof.total_ms[kernel];
+  *launches = c->prof.launches[kernel];
+  return 0;
+}
+int64_t semb_launch_count(semb_ctx* c) { return c ? c->launch_count : -1; }
+
+}  // extern "C"

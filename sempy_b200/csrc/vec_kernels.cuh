@@ -1,0 +1,305 @@
+// K2 (gather-scatter), K3/K4 (fused CG vector updates) and the scalar kernels.
+#pragma once
+
+#include "common.cuh"
+
+namespace semb {
+
+constexpr int VEC_NT = 256;
+
+// ---------------------------------------------------------------------------
+// K2: direct-stiffness summation, atomic-free.
+//
+// Replaces gslib's gs(x, gs_double, gs_add) as SemPy calls it
+// (sempy/mesh.py:444-447; semantics stated by python_gather_scatter,
+// sempy/loopy/loopy_kernels.py:26-39).  The schedule holds only segments with
+// more than one local copy, grouped by length so that one thread owns one
+// segment, fetches its indices with a single vector load, sums the copies in
+// ascending local index (fixed order -> bitwise repeatable) and writes the sum
+// back to every copy.  Traffic: 8 + 4 + 8 bytes per shared local node.
+// ---------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(VEC_NT)
+gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t nseg, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  for (int64_t s = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * VEC_NT) {
+    int id[L];
+    if (L == 2) {
+      const int2 v = __ldg(reinterpret_cast<const int2*>(ids) + s);
+      id[0] = v.x;
+      id[1] = v.y;
+    } else {
+#pragma unroll
+      for (int c = 0; c < L / 4; ++c) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(ids) + s * (L / 4) + c);
+        id[4 * c] = v.x;
+        id[4 * c + 1] = v.y;
+        id[4 * c + 2] = v.z;
+        id[4 * c + 3] = v.w;
+      }
+    }
+    double v[L];
+#pragma unroll
+    for (int c = 0; c < L; ++c) v[c] = x[id[c]];
+    double sum = v[0];
+#pragma unroll
+    for (int c = 1; c < L; ++c) sum += v[c];
+#pragma unroll
+    for (int c = 0; c < L; ++c) x[id[c]] = sum;
+  }
+}
+
+// Segments of any other length (unstructured meshes): CSR offsets.
+__global__ void __launch_bounds__(VEC_NT)
+gs_var_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const int32_t* __restrict__ start,
+              int64_t nseg, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  for (int64_t s = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * VEC_NT) {
+    const int lo = start[s], hi = start[s + 1];
+    double sum = 0.0;
+    for (int q = lo; q < hi; ++q) sum += x[ids[q]];
+    for (int q = lo; q < hi; ++q) x[ids[q]] = sum;
+  }
+}
+
+// x[mask_ids] = 0   (Mesh.apply_mask, sempy/mesh.py:487-494, as an index list)
+__global__ void mask_kernel(double* __restrict__ x, const int64_t* __restrict__ ids, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    x[ids[q]] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// Reductions: every CTA writes one partial; a single CTA sums them in a fixed
+// order (bitwise repeatable, no atomics).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double s_red[VEC_NT / 32];
+  __shared__ double s_out;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < VEC_NT / 32; ++q) s += s_red[q];
+    s_out = s;
+  }
+  __syncthreads();
+  return s_out;
+}
+
+// out[q] = sum(partials[q*stride .. q*stride + n)) for q < nout (one CTA).
+__global__ void __launch_bounds__(VEC_NT)
+reduce_partials_kernel(const double* __restrict__ partials, int64_t n, int64_t stride, int nout,
+                       double* __restrict__ out, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  for (int q = 0; q < nout; ++q) {
+    double v = 0.0;
+    for (int64_t t = threadIdx.x; t < n; t += VEC_NT) v += partials[q * stride + t];
+    const double s = block_sum(v);
+    if (threadIdx.x == 0) out[q] = s;
+    __syncthreads();
+  }
+}
+
+// dot with optional weight: partials[b] = sum_b w x y
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(VEC_NT)
+dot_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ wgt, int64_t n,
+           double* __restrict__ partials) {
+  double acc = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n; q += (int64_t)gridDim.x * VEC_NT)
+    acc = fma(WEIGHTED ? wgt[q] * x[q] : x[q], y[q], acc);
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------
+// CG set-up:  x = 0, r = b, p = z = Minv r;  partial sums of |b|_w^2 and r.z
+// (sempy/elliptic.py:31-46; sempy/iterative.py:48-63 for the PCG form).
+// ---------------------------------------------------------------------------
+template <bool JACOBI>
+__global__ void __launch_bounds__(VEC_NT)
+cg_init_kernel(const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+               const double* __restrict__ rmult, const double* __restrict__ dinv, int64_t n,
+               double* __restrict__ partials) {
+  double nb = 0.0, rz = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n; q += (int64_t)gridDim.x * VEC_NT) {
+    const double bq = b[q];
+    const double wb = rmult[q] * bq;
+    nb = fma(wb, bq, nb);
+    double z = bq;
+    if (JACOBI) {
+      z = dinv[q] * bq;
+      rz = fma(wb, z, rz);
+    }
+    x[q] = 0.0;
+    r[q] = bq;
+    p[q] = z;
+  }
+  const double s0 = block_sum(nb);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s0;
+  if (JACOBI) {
+    __syncthreads();
+    const double s1 = block_sum(rz);
+    if (threadIdx.x == 0) partials[gridDim.x + blockIdx.x] = s1;
+  }
+}
+
+// two[0] = |b|_w^2, two[1] = r.z (Jacobi only)
+__global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double tol, int maxit, int jacobi) {
+  const double norm_b = two[0];
+  const double rdotr = jacobi ? two[1] : norm_b;
+  s->norm_b = norm_b;
+  s->TOL = fmax(tol * tol * norm_b, tol * tol);
+  s->rdotr = rdotr;
+  s->rdotr_new = rdotr;
+  s->pAp = 0.0;
+  s->alpha = 0.0;
+  s->beta = 0.0;
+  s->niter = 0;
+  s->maxit = maxit;
+  // elliptic.py:43 early-out (CG only; pcg has none) and the loop condition :47 / iterative.py:61
+  const bool early = (!jacobi) && (rdotr < 1.0e-20);
+  s->done = (early || !(0 < maxit && rdotr > s->TOL)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// K3: x += alpha p ; r -= alpha Ap ; partial of sum rmult r r (or rmult r dinv r)
+// (sempy/elliptic.py:52-60; iterative.py:66-73).  56 B per node (+8 Jacobi).
+// ---------------------------------------------------------------------------
+template <bool JACOBI>
+__global__ void __launch_bounds__(VEC_NT)
+cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                 const double* __restrict__ Ap, const double* __restrict__ rmult, const double* __restrict__ dinv,
+                 const CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials) {
+  if (s->done) return;
+  const double alpha = s->rdotr / s->pAp;
+  double acc = 0.0;
+  const int64_t n2 = n >> 1;
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+  const double2* a2 = reinterpret_cast<const double2*>(Ap);
+  const double2* m2 = reinterpret_cast<const double2*>(rmult);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
+    const double2 pv = p2[q], av = a2[q], mv = m2[q];
+    double2 xv = x2[q], rv = r2[q];
+    xv.x = xv.x + alpha * pv.x;
+    xv.y = xv.y + alpha * pv.y;
+    rv.x = rv.x - alpha * av.x;
+    rv.y = rv.y - alpha * av.y;
+    x2[q] = xv;
+    r2[q] = rv;
+    if (JACOBI) {
+      const double2 dv = d2[q];
+      acc = fma(mv.x * rv.x, dv.x * rv.x, acc);
+      acc = fma(mv.y * rv.y, dv.y * rv.y, acc);
+    } else {
+      acc = fma(mv.x * rv.x, rv.x, acc);
+      acc = fma(mv.y * rv.y, rv.y, acc);
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t q = n - 1;
+    const double xv = x[q] + alpha * p[q];
+    const double rv = r[q] - alpha * Ap[q];
+    x[q] = xv;
+    r[q] = rv;
+    acc = fma(rmult[q] * rv, JACOBI ? dinv[q] * rv : rv, acc);
+  }
+  const double sum = block_sum(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = sum;
+}
+
+// After the update's reduction: beta, history, iteration count, stop test
+// (sempy/elliptic.py:47,59-71).
+__global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
+  if (s->done) return;
+  const double r0 = s->rdotr, r1 = s->rdotr_new;
+  const double alpha = r0 / s->pAp;
+  const double beta = r1 / r0;
+  if (hist != nullptr) {
+    double* h = hist + 5 * (int64_t)s->niter;
+    h[0] = r0;
+    h[1] = r1;
+    h[2] = alpha;
+    h[3] = beta;
+    h[4] = s->pAp;
+  }
+  s->alpha = alpha;
+  s->beta = beta;
+  s->rdotr = r1;
+  s->niter += 1;
+  s->done = !(s->niter < s->maxit && r1 > s->TOL) ? 1 : 0;
+}
+
+// K4: p = z + beta p with z = r or dinv r (sempy/elliptic.py:70; iterative.py:83). 24 B per node.
+template <bool JACOBI>
+__global__ void __launch_bounds__(VEC_NT)
+cg_direction_kernel(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ dinv,
+                    const CgScalars* __restrict__ s, int64_t n) {
+  if (s->done) return;
+  const double beta = s->beta;
+  const int64_t n2 = n >> 1;
+  double2* p2 = reinterpret_cast<double2*>(p);
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
+    double2 pv = p2[q];
+    double2 zv = r2[q];
+    if (JACOBI) {
+      const double2 dv = d2[q];
+      zv.x *= dv.x;
+      zv.y *= dv.y;
+    }
+    pv.x = zv.x + beta * pv.x;
+    pv.y = zv.y + beta * pv.y;
+    p2[q] = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t q = n - 1;
+    const double z = JACOBI ? dinv[q] * r[q] : r[q];
+    p[q] = z + beta * p[q];
+  }
+}
+
+// dinv = mask ? 0 : 1/diag   (Jacobi preconditioner on assembled diagonal)
+__global__ void jacobi_invert_kernel(double* __restrict__ d, const uint32_t* __restrict__ maskbits, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const bool masked = maskbits != nullptr && ((maskbits[q >> 5] >> (q & 31)) & 1u);
+    d[q] = masked ? 0.0 : 1.0 / d[q];
+  }
+}
+
+// rmult = 1 / count  (sempy/mesh.py:440-442): fill with ones, gather-scatter, invert
+__global__ void fill_kernel(double* __restrict__ x, double v, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) x[q] = v;
+}
+__global__ void reciprocal_kernel(double* __restrict__ x, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    x[q] = 1.0 / x[q];
+}
+
+// ---- generic-operator CG pieces (sempy/iterative.py) ----------------------
+// x += a p ; r -= a Ap  with a = num/den read from device memory
+__global__ void __launch_bounds__(VEC_NT)
+axpy_pair_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                 const double* __restrict__ Ap, const double* num, const double* den, int64_t n) {
+  const double a = *num / *den;
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n; q += (int64_t)gridDim.x * VEC_NT) {
+    x[q] = x[q] + a * p[q];
+    r[q] = r[q] - a * Ap[q];
+  }
+}
+// p = z + (num/den) p
+__global__ void __launch_bounds__(VEC_NT)
+xpby_kernel(double* __restrict__ p, const double* __restrict__ z, const double* num, const double* den, int64_t n) {
+  const double bcoef = *num / *den;
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n; q += (int64_t)gridDim.x * VEC_NT)
+    p[q] = z[q] + bcoef * p[q];
+}
+
+}  // namespace semb

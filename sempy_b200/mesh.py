@@ -1,0 +1,437 @@
+"""Hex mesh with GLL nodes: set-up on the host, hot-path state on the GPU.
+
+Drop-in for the ``Mesh`` of sempy/mesh.py (same constructor, method names and
+attributes): ``find_physical_coordinates``, ``calc_geometric_factors``,
+``establish_global_numbering``, ``setup_mask``, ``dssum``, ``apply_mask`` and
+the getters.  Differences that matter:
+
+* no ``meshio`` / ``gslib_wrapper``: a gmsh-2.2 ASCII reader is built in and the
+  gather-scatter is the atomic-free CUDA kernel of libsemb200 (``semb_gs``);
+* set-up is vectorised (no per-node Python loops) and the tensor contractions
+  in it run on the GPU (``semb_kron``, ``semb_gradient``);
+* ``dssum`` / ``apply_mask`` / ``elliptic_ax`` / ``elliptic_cg`` use a device
+  context (``semb_ctx``) that holds D, the six geometric factors, the
+  gather-scatter schedule and the mask bits; it is built on first use.
+
+Vectors handed to ``dssum``/``apply_mask`` may be NumPy arrays (updated in
+place through a host<->device copy, as the reference's callers expect) or
+torch CUDA tensors (updated in place on the device, no copies).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from sempy_b200 import _capi
+from sempy_b200.derivative import reference_derivative_matrix
+from sempy_b200.gradient import gradient
+from sempy_b200.interpolation import lagrange
+from sempy_b200.kron import kron
+from sempy_b200.mass import reference_mass_matrix_3d
+from sempy_b200.quadrature import gauss_lobatto
+
+# gmsh hexahedron vertex order -> lexicographic (i fastest); sempy/mesh.py:272-274
+_GMSH_TO_LEX = [0, 1, 3, 2, 4, 5, 7, 6]
+
+
+def read_gmsh22(fname):
+    """gmsh 2.2 ASCII: vertices (nv,3) and 8-node hexahedra (E,8), 0-based.
+    Takes the place of meshio.read in sempy/mesh.py:102-110."""
+    with open(fname) as fh:
+        lines = fh.read().splitlines()
+    pos = 0
+    points = None
+    hexes = []
+    nquads = 0
+    while pos < len(lines):
+        tag = lines[pos].strip()
+        pos += 1
+        if tag == "$MeshFormat":
+            version = lines[pos].split()
+            if not version[0].startswith("2") or version[1] != "0":
+                raise Exception("Only gmsh 2.x ASCII meshes are supported")
+        elif tag == "$Nodes":
+            count = int(lines[pos])
+            block = np.array([ln.split() for ln in lines[pos + 1: pos + 1 + count]], dtype=np.float64)
+            points = np.zeros((count, 3))
+            points[block[:, 0].astype(np.int64) - 1] = block[:, 1:4]
+            pos += 1 + count
+        elif tag == "$Elements":
+            count = int(lines[pos])
+            for ln in lines[pos + 1: pos + 1 + count]:
+                f = ln.split()
+                etype, ntags = int(f[1]), int(f[2])
+                if etype == 5:
+                    hexes.append([int(v) - 1 for v in f[3 + ntags: 3 + ntags + 8]])
+                elif etype == 3:
+                    nquads += 1
+            pos += 1 + count
+    if points is None:
+        raise Exception(f"{fname}: no $Nodes section")
+    return points, np.array(hexes, dtype=np.int64).reshape(-1, 8), nquads
+
+
+def write_gmsh22(fname, points, hexes):
+    """Write vertices and hexahedra as gmsh 2.2 ASCII (full double precision)."""
+    with open(fname, "w") as fh:
+        fh.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(points))
+        for q, pt in enumerate(points):
+            fh.write("%d %r %r %r\n" % (q + 1, float(pt[0]), float(pt[1]), float(pt[2])))
+        fh.write("$EndNodes\n$Elements\n%d\n" % len(hexes))
+        for q, h in enumerate(hexes):
+            fh.write("%d 5 2 2 1 %s\n" % (q + 1, " ".join(str(int(v) + 1) for v in h)))
+        fh.write("$EndElements\n")
+
+
+def box_mesh_arrays(nx, ny=None, nz=None, perturb=0.0, seed=0):
+    """Vertices/hexes of an nx*ny*nz box on [0,1]^3, elements i-fastest and
+    k-slowest (z-slabs are contiguous element ranges); ``perturb`` displaces the
+    interior vertices by perturb*h*(U(0,1)-0.5) per axis (full 3x3 G)."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    gx, gy, gz = (np.linspace(0.0, 1.0, m + 1) for m in (nx, ny, nz))
+    Z, Y, X = np.meshgrid(gz, gy, gx, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    if perturb:
+        rng = np.random.default_rng(seed)
+        h = np.array([1.0 / nx, 1.0 / ny, 1.0 / nz])
+        shift = perturb * h * (rng.random(pts.shape) - 0.5)
+        kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+        inner = ((ii > 0) & (ii < nx) & (jj > 0) & (jj < ny) & (kk > 0) & (kk < nz)).ravel()
+        pts[inner] += shift[inner]
+    k, j, i = (a.ravel() for a in np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij"))
+    sx, sy = nx + 1, (nx + 1) * (ny + 1)
+    base = k * sy + j * sx + i
+    hexes = np.stack([base, base + 1, base + 1 + sx, base + sx,
+                      base + sy, base + 1 + sy, base + 1 + sx + sy, base + sx + sy], axis=1).astype(np.int64)
+    return pts, hexes
+
+
+def global_numbering_from_coordinates(xe, ye, ze, tol=1e-12):
+    """The reference's numbering rule (sempy/mesh.py:389-435), vectorised:
+    stable lexicographic sort of all local nodes by exact (x, y, z), new id
+    whenever the squared distance to the next sorted point exceeds ``tol``,
+    ids from 1.  Returns (global_id int32 (E,Np), global_to_local int64,
+    global_start int64) -- bit-identical to the reference's Python-object sort
+    for the same coordinates."""
+    E, Np = xe.shape
+    size = E * Np
+    x, y, z = xe.reshape(-1), ye.reshape(-1), ze.reshape(-1)
+    order = np.lexsort((z, y, x)).astype(np.int64)  # last key is primary; lexsort is stable
+    sx, sy, sz = x[order], y[order], z[order]
+    gap = (sx[:-1] - sx[1:]) ** 2 + (sy[:-1] - sy[1:]) ** 2 + (sz[:-1] - sz[1:]) ** 2 > tol
+    ids = np.empty(size, dtype=np.int32)
+    ids[order] = np.concatenate(([1], 1 + np.cumsum(gap, dtype=np.int64))).astype(np.int32)
+    start = np.concatenate(([0], np.flatnonzero(gap) + 1, [size])).astype(np.int64)
+    return ids.reshape(E, Np), order, start
+
+
+def bounding_box_mask(xe, ye, ze, tol=1e-8):
+    """0 where any coordinate is within ``tol`` of the global bounding box
+    (homogeneous Dirichlet), else 1; sempy/mesh.py:449-477, flat (E*Np,)."""
+    mask = np.ones(xe.shape)
+    for c in (xe, ye, ze):
+        mask[np.abs(c - np.min(c)) < tol] = 0
+        mask[np.abs(c - np.max(c)) < tol] = 0
+    return mask.reshape(-1)
+
+
+class _Context:
+    """Owner of one semb_ctx; frees it with the mesh."""
+
+    def __init__(self, device, nelem, Nq):
+        self.lib = _capi.lib()
+        _capi.require_gpu()
+        self.device = device
+        handle = C.c_void_p()
+        _capi.check(self.lib.semb_create(C.byref(handle), device, nelem, Nq))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.semb_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Mesh:
+    def __init__(self, fname, debug=0):
+        if not isinstance(fname, str):
+            raise Exception("Only strings are allowed for file name")
+        self.debug = debug
+        self._reset_device_state()
+        self.read(fname)
+
+    # -- construction -------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, points, hexes, debug=0):
+        """Build from vertex coordinates (nv,3) and hexahedra (E,8) in gmsh order."""
+        self = cls.__new__(cls)
+        self.debug = debug
+        self._reset_device_state()
+        self._set_topology(np.asarray(points, dtype=np.float64), np.asarray(hexes, dtype=np.int64))
+        return self
+
+    def _reset_device_state(self):
+        self._ctx = None
+        self._dirty = {"D": True, "geom": True, "gs": True, "mask": True}
+        self.geom6 = None
+        self.global_to_local = None
+        self.mask = None
+
+    def read(self, fname):
+        points, hexes, nquads = read_gmsh22(fname)
+        if len(hexes) == 0:
+            if nquads:
+                raise Exception("2D not supported yet.")
+            raise Exception(f"{fname}: no hexahedra")
+        self._set_topology(points, hexes)
+
+    def _set_topology(self, points, hexes):
+        assert len(hexes) > 0 and len(points) > 0
+        self.elem_to_vert_map = hexes
+        self.num_elements = hexes.shape[0]
+        self.num_verts = hexes.shape[1]
+        self.ndim = points.shape[1]
+        if self.ndim != 3:
+            raise Exception("2D not supported yet.")
+        self.num_faces = 2 * self.ndim
+        self.nface_verts = self.ndim + 1
+        self.face_to_vert_map = np.array(
+            [[0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [0, 1, 2, 3], [4, 5, 6, 7]]
+        )
+        self.x = points[hexes, 0]
+        self.y = points[hexes, 1]
+        self.z = points[hexes, 2]
+
+    # -- simple getters (sempy/mesh.py:167-186) -------------------------------
+    def get_num_elems(self):
+        return self.num_elements
+
+    def get_ndim(self):
+        return self.ndim
+
+    def get_num_faces(self):
+        return self.num_faces
+
+    def get_num_verts(self):
+        return self.num_verts
+
+    def get_face_to_vert_map(self):
+        return self.face_to_vert_map
+
+    def get_elem_to_vert_map(self):
+        return self.elem_to_vert_map
+
+    def get_num_face_verts(self):
+        return self.nface_verts
+
+    # -- set-up ---------------------------------------------------------------
+    def find_physical_coordinates(self, N):
+        """GLL coordinates by trilinear interpolation of the 8 vertices
+        (sempy/mesh.py:247-302): one batched kron launch per coordinate."""
+        self.N = N
+        self.Nq = N + 1
+        self.Nfp = (N + 1) * (N + 1)
+        self.Np = (N + 1) ** 3
+        z_1, _ = gauss_lobatto(1)
+        z_N, _ = gauss_lobatto(N)
+        J = lagrange(z_N, z_1)
+        self.xe = kron(J, J, J, self.x[:, _GMSH_TO_LEX])
+        self.ye = kron(J, J, J, self.y[:, _GMSH_TO_LEX])
+        self.ze = kron(J, J, J, self.z[:, _GMSH_TO_LEX])
+        self._reset_device_state()
+
+    def calc_geometric_factors(self):
+        """G = (grad a . grad b) B J, Jacobian and mass per node
+        (sempy/mesh.py:304-356), vectorised over all elements; the nine
+        coordinate derivatives come from the batched GPU gradient."""
+        n = self.Nq
+        D = reference_derivative_matrix(self.N)
+        xr, xs, xt = gradient(self.xe, n, D)
+        yr, ys, yt = gradient(self.ye, n, D)
+        zr, zs, zt = gradient(self.ze, n, D)
+        J = xr * (ys * zt - yt * zs) - yr * (xs * zt - xt * zs) + zr * (xs * yt - ys * xt)
+        rx = (ys * zt - yt * zs) / J
+        sx = (yt * zr - yr * zt) / J
+        tx = (yr * zs - ys * zr) / J
+        ry = -(zt * xs - zs * xt) / J
+        sy = -(zr * xt - zt * xr) / J
+        ty = -(zs * xr - zr * xs) / J
+        rz = (xs * yt - xt * ys) / J
+        sz = -(xr * yt - xt * yr) / J
+        tz = (xr * ys - xs * yr) / J
+        del xr, xs, xt, yr, ys, yt, zr, zs, zt
+        B = reference_mass_matrix_3d(self.N)
+        E, Np = self.xe.shape
+        g6 = np.empty((E, 6, Np))
+        g6[:, 0] = (rx * rx + ry * ry + rz * rz) * B * J
+        g6[:, 1] = (rx * sx + ry * sy + rz * sz) * B * J
+        g6[:, 2] = (rx * tx + ry * ty + rz * tz) * B * J
+        g6[:, 3] = (sx * sx + sy * sy + sz * sz) * B * J
+        g6[:, 4] = (sx * tx + sy * ty + sz * tz) * B * J
+        g6[:, 5] = (tx * tx + ty * ty + tz * tz) * B * J
+        self.geom6 = g6
+        self.jaco = J
+        self._B = B
+        self._dirty["geom"] = True
+
+    @property
+    def geom(self):
+        """(E,3,3,Np) view of the geometric factors as the reference stores them."""
+        return self.geom6[:, [[0, 1, 2], [1, 3, 4], [2, 4, 5]], :]
+
+    @property
+    def mass(self):
+        return np.broadcast_to(self._B, (self.num_elements, self.Np))
+
+    def establish_global_numbering(self):
+        """Global ids by coordinate sort (sempy/mesh.py:389-442); the gslib
+        handle of the reference becomes the device gather-scatter schedule."""
+        self.global_id, self.global_to_local, self.global_start = global_numbering_from_coordinates(
+            self.xe, self.ye, self.ze
+        )
+        self._dirty["gs"] = True
+        self.rmult = np.empty(self.num_elements * self.Np, dtype=np.float64)
+        ctx = self._context(need=("gs",))
+        _capi.check(ctx.lib.semb_get_rmult(ctx.handle, self.rmult.ctypes.data, _capi.HOST))
+
+    def setup_mask(self):
+        self.mask = bounding_box_mask(self.xe, self.ye, self.ze)
+        self._dirty["mask"] = True
+
+    # -- device context ---------------------------------------------------------
+    def _context(self, need=("D", "geom", "gs", "mask")):
+        if self._ctx is None:
+            self._ctx = _Context(_capi.current_device(), self.num_elements, self.Nq)
+            self._dirty = {k: True for k in self._dirty}
+        ctx, lib = self._ctx, self._ctx.lib
+        for key in need:
+            if not self._dirty[key]:
+                continue
+            if key == "D":
+                D = _capi.as_f64(reference_derivative_matrix(self.N))
+                _capi.check(lib.semb_set_derivative(ctx.handle, D.ctypes.data))
+            elif key == "geom":
+                if self.geom6 is None:
+                    raise RuntimeError("call calc_geometric_factors() first")
+                g6 = _capi.as_f64(self.geom6)
+                _capi.check(lib.semb_set_geom(ctx.handle, g6.ctypes.data, _capi.G6, _capi.HOST))
+            elif key == "gs":
+                if self.global_to_local is None:
+                    raise RuntimeError("call establish_global_numbering() first")
+                g2l = np.ascontiguousarray(self.global_to_local, dtype=np.int64)
+                gst = np.ascontiguousarray(self.global_start, dtype=np.int64)
+                _capi.check(lib.semb_set_gather_scatter(ctx.handle, g2l.ctypes.data, gst.ctypes.data, gst.size - 1))
+            elif key == "mask":
+                if self.mask is None:
+                    raise RuntimeError("call setup_mask() first")
+                ids = np.ascontiguousarray(self.get_mask_ids(), dtype=np.int64)
+                _capi.check(lib.semb_set_mask(ctx.handle, ids.ctypes.data, ids.size))
+            self._dirty[key] = False
+        return ctx
+
+    def _vector_args(self, x, name):
+        """(pointer, mem flag, keep-alive) for an in-place vector argument."""
+        size = self.num_elements * self.Np
+        if _capi.is_torch_cuda(x):
+            import torch
+
+            if x.dtype != torch.float64 or not x.is_contiguous() or x.numel() != size:
+                raise ValueError(f"{name}: need a contiguous float64 CUDA tensor of {size} entries")
+            return x.data_ptr(), _capi.DEVICE, x
+        if not isinstance(x, np.ndarray) or x.dtype != np.float64 or not x.flags.c_contiguous or x.size != size:
+            raise ValueError(f"{name}: need a C-contiguous float64 NumPy array of {size} entries")
+        return x.ctypes.data, _capi.HOST, x
+
+    def _bind_stream(self, ctx, mem):
+        if mem == _capi.DEVICE:
+            import torch
+
+            _capi.check(ctx.lib.semb_set_stream(ctx.handle, torch.cuda.current_stream().cuda_stream))
+        else:
+            _capi.check(ctx.lib.semb_set_stream(ctx.handle, None))
+
+    # -- hot-path operations ------------------------------------------------------
+    def dssum(self, x):
+        """In-place direct-stiffness sum, returns x (sempy/mesh.py:444-447)."""
+        ctx = self._context(need=("gs",))
+        p, mem, _keep = self._vector_args(x, "dssum")
+        self._bind_stream(ctx, mem)
+        _capi.check(ctx.lib.semb_gs(ctx.handle, p, mem))
+        return x
+
+    def apply_mask(self, x):
+        """In-place x[mask == 0] = 0, returns x (sempy/mesh.py:487-494)."""
+        ctx = self._context(need=("mask",))
+        p, mem, _keep = self._vector_args(x, "apply_mask")
+        self._bind_stream(ctx, mem)
+        _capi.check(ctx.lib.semb_mask(ctx.handle, p, mem))
+        return x
+
+    def operator(self, mask=True, assemble=True):
+        """Device operator p -> [dssum][mask] A p for sempy_b200.iterative.cg/pcg."""
+        return _DeviceOperator(self, mask, assemble)
+
+    # -- getters (sempy/mesh.py:479-527) --------------------------------------------
+    def get_global_to_local_map(self):
+        return self.global_to_local, self.global_start
+
+    def get_mask_ids(self):
+        return np.flatnonzero(self.mask == 0)
+
+    def get_x(self):
+        return self.xe.reshape((self.num_elements * self.Np,))
+
+    def get_y(self):
+        return self.ye.reshape((self.num_elements * self.Np,))
+
+    def get_z(self):
+        return self.ze.reshape((self.num_elements * self.Np,))
+
+    def get_rmult(self):
+        return self.rmult
+
+    def get_geom(self):
+        return np.array(self.geom).reshape((self.num_elements, self.ndim, self.ndim, self.Np))
+
+    def get_jaco(self):
+        return np.array(self.jaco).reshape((self.num_elements * self.Np,))
+
+    def get_mass(self):
+        return np.array(self.mass).reshape((self.num_elements * self.Np,))
+
+
+class _DeviceOperator:
+    """A as a device callback: used by iterative.cg/pcg without host copies."""
+
+    def __init__(self, mesh, mask, assemble):
+        self.mesh = mesh
+        self.flags = (_capi.AX_MASK if mask else 0) | (_capi.AX_GS if assemble else 0)
+
+    def apply_device(self, d_in, d_out, n):
+        need = ["D", "geom"] + (["mask"] if self.flags & _capi.AX_MASK else []) + (["gs"] if self.flags & _capi.AX_GS else [])
+        ctx = self.mesh._context(need=tuple(need))
+        _capi.check(ctx.lib.semb_ax(ctx.handle, d_in, d_out, self.flags, _capi.DEVICE))
+        _capi.check(ctx.lib.semb_synchronize(ctx.handle))
+
+    def __call__(self, p):
+        from sempy_b200.elliptic import _ax
+
+        return _ax(self.mesh, p, self.flags)
+
+
+def load_mesh(fname):
+    """Mesh from the package's ``meshes`` directory (sempy/mesh.py:530-533)."""
+    dir_path = os.path.dirname(os.path.realpath(__file__))
+    return Mesh(os.path.join(dir_path, "meshes", fname))
+
+
+def box_mesh(nx, ny=None, nz=None, perturb=0.0, seed=0):
+    """Synthetic box mesh without a file round trip."""
+    return Mesh.from_arrays(*box_mesh_arrays(nx, ny, nz, perturb, seed))

@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against the
+golden outputs of the unmodified reference and against the CPU oracle on
+seeded inputs.  Tolerances are the ones BASELINE.json states: numbering
+bit-exact, Ax relative inf-norm <= 1e-12, CG iteration count +-1, solution
+<= 1e-10 relative."""
+
+import numpy as np
+import pytest
+
+from conftest import MESH_CASES, load_golden, rel_inf
+from oracle import sem_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+AX_TOL = 1e-12
+UNIT_N = (1, 2, 3, 4, 7, 10, 15)
+
+
+def golden_mesh(g, own_geometry=False):
+    """Product Mesh carrying the reference's own arrays (same D, G, numbering
+    and mask feed both paths) or, with own_geometry, built by the product."""
+    from sempy_b200.mesh import Mesh
+
+    m = Mesh.from_arrays(g["points"], g["hexes"])
+    N = int(g["N"])
+    m.find_physical_coordinates(N)
+    if not own_geometry:
+        m.xe, m.ye, m.ze = g["xe"].copy(), g["ye"].copy(), g["ze"].copy()
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    if not own_geometry:
+        m.geom6 = g["geom6"].copy()
+        m._dirty["geom"] = True
+    m.setup_mask()
+    return m
+
+
+@pytest.mark.parametrize("N", UNIT_N)
+def test_gradient_kernels(units, N):
+    from sempy_b200.gradient import gradient, gradient_transpose
+
+    n = N + 1
+    got = np.stack(gradient(units[f"grad_U_{N}"], n, units[f"D_{N}"]))
+    assert rel_inf(got, units[f"grad_out_{N}"]) < 1e-13
+    W = units[f"gradT_W_{N}"]
+    assert rel_inf(gradient_transpose(W[0], W[1], W[2], n, units[f"D_{N}"]), units[f"gradT_out_{N}"]) < 1e-13
+    # default D (rebuilt from the order, as the reference does) and batched input
+    got = np.stack(gradient(units[f"grad_U_{N}"], n))
+    assert rel_inf(got, units[f"grad_out_{N}"]) < 1e-11
+    batch = np.stack([units[f"grad_U_{N}"], 2.0 * units[f"grad_U_{N}"]])
+    ur, us, ut = gradient(batch, n, units[f"D_{N}"])
+    assert ur.shape == batch.shape and rel_inf(ur[1], 2.0 * units[f"grad_out_{N}"][0]) < 1e-13
+
+
+def test_kron_kernel(units):
+    from sempy_b200.kron import kron, kron_2d
+
+    Sz, Sy, Sx, U = units["kron_Sz"], units["kron_Sy"], units["kron_Sx"], units["kron_U"]
+    assert rel_inf(kron(Sz, Sy, Sx, U), units["kron_out"]) < 1e-14
+    assert rel_inf(kron(Sz, Sy, Sx, U, order="C"), units["kron_out"]) < 1e-14
+    ref_f = np.einsum("ai,bj,ijk,ck->abc", Sz, Sy, U.reshape((2, 3, 4), order="F"), Sx).reshape(-1, order="F")
+    assert rel_inf(kron(Sz, Sy, Sx, U, order="F"), ref_f) < 1e-14
+    U2 = U[:12]
+    assert rel_inf(kron_2d(Sy, Sx, U2), (Sy @ U2.reshape(3, 4) @ Sx.T).reshape(-1)) < 1e-14
+
+
+def test_generic_cg_known_answers(units):
+    """reference tests/cg_test.py:6-34 and a fixed SPD system, through the CUDA vector kernels."""
+    from sempy_b200.iterative import cg, pcg
+
+    A = np.array([[4.0, 1.0], [1.0, 3.0]])
+    x, it = cg(lambda v: A @ v, np.array([1.0, 2.0]))
+    assert it <= 2 and (np.round(x, 4) == np.array([0.0909, 0.6364])).all()
+    A3 = np.array([1.0, 2.0, -1.0, 2.0, 2.0, 2.0, 1.0, -1.0, 2.0]).reshape(3, 3)
+    A3 = (A3 + A3.T) / 2.0
+    b3 = np.array([2.0, 12.0, 5.0])
+    x, it = cg(lambda v: A3 @ v, b3)
+    assert it <= 3 and np.allclose(x, np.linalg.solve(A3, b3), atol=1e-8)
+    A, b = units["it_A"], units["it_b"]
+    x, it = cg(lambda v: A @ v, b, tol=1e-12, maxit=100)
+    assert abs(it - int(units["it_cg_niter"])) <= 1 and rel_inf(x, units["it_cg_x"]) < 1e-10
+    dA = np.diag(A).copy()
+    x, it = pcg(lambda v: A @ v, lambda r: r / dA, b, tol=1e-10, maxit=100)
+    assert abs(it - int(units["it_pcg_niter"])) <= 1 and rel_inf(x, units["it_pcg_x"]) < 1e-9
+    x, it = cg(lambda v: A @ v, np.zeros(12))  # early-out, iterative.py:15
+    assert it == 0 and not x.any()
+    with pytest.raises(AssertionError):
+        pcg(lambda v: v, lambda v: v, np.zeros((2, 2)))
+    with pytest.raises(ZeroDivisionError):
+        cg(lambda v: 1 / 0, np.ones(3))
+
+
+@pytest.mark.parametrize("case", MESH_CASES)
+def test_setup_matches_reference(case):
+    g = load_golden(case)
+    m = golden_mesh(g, own_geometry=True)
+    for got, ref in ((m.xe, g["xe"]), (m.ye, g["ye"]), (m.ze, g["ze"])):
+        assert np.max(np.abs(got - ref)) < 1e-14
+    assert np.max(np.abs(m.geom6 - g["geom6"])) <= 1e-12 * np.abs(g["geom6"]).max()
+    assert np.allclose(m.get_jaco(), g["jaco"].reshape(-1), rtol=1e-11)
+    assert m.get_geom().shape == (g["hexes"].shape[0], 3, 3, m.Np)
+    assert np.allclose(m.get_mass()[: m.Np], g["mass0"], rtol=1e-13)
+    assert m.global_id.max() == g["global_id"].max()
+    assert np.array_equal(np.sort(m.get_rmult()), np.sort(g["rmult"]))
+
+
+@pytest.mark.parametrize("case", MESH_CASES)
+def test_ax_gs_mask_vs_reference(case):
+    from sempy_b200.elliptic import elliptic_ax
+
+    g = load_golden(case)
+    m = golden_mesh(g)
+    assert np.array_equal(m.global_id, g["global_id"]) and np.array_equal(m.get_rmult(), g["rmult"])
+    assert np.array_equal(m.get_mask_ids(), g["mask_ids"])
+    ax = elliptic_ax(m, g["p"])
+    assert ax is not g["p"] and rel_inf(ax, g["ax_raw"]) <= AX_TOL
+    x = g["p"].copy()
+    assert m.dssum(x) is x  # in place, returns its argument (mesh.py:444-447)
+    assert rel_inf(x * m.get_rmult(), g["p_cont"]) < 1e-15
+    full = m.dssum(m.apply_mask(elliptic_ax(m, g["p_cont"])))
+    assert rel_inf(full, g["ax_full"]) <= AX_TOL
+    y = g["p"].copy()
+    m.apply_mask(y)
+    assert np.array_equal(y, g["p"] * g["mask"])
+
+
+@pytest.mark.parametrize("case", MESH_CASES)
+def test_cg_vs_reference(case):
+    from sempy_b200.elliptic import elliptic_cg, elliptic_pcg
+
+    g = load_golden(case)
+    m = golden_mesh(g)
+    for tol in ("1e-08", "1e-10"):
+        x, it = elliptic_cg(m, g["b"], tol=float(tol), maxit=10000)
+        assert abs(it - int(g["cg_niter_" + tol])) <= 1, (it, int(g["cg_niter_" + tol]))
+        if it == int(g["cg_niter_" + tol]):
+            assert rel_inf(x, g["cg_x_" + tol]) < 1e-10
+    x, it = elliptic_pcg(m, g["b"], tol=1e-10, maxit=10000)
+    assert abs(it - int(g["pcg_niter_1e-10"])) <= 1
+    assert rel_inf(x, g["pcg_x_1e-10"]) < 1e-8
+    # tight solve: the solution itself to 1e-10 against the oracle at the same tolerance
+    geom = so_geom9(g)
+    axo = lambda p: so.elliptic_ax_batched(geom, p, int(g["N"]), g["D"])
+    xo, ito = so.elliptic_cg(axo, g["mask"], g["global_to_local"], g["global_start"], g["rmult"], g["b"], tol=1e-12, maxit=5000)
+    x, it = elliptic_cg(m, g["b"], tol=1e-12, maxit=5000)
+    assert abs(it - ito) <= 1 and rel_inf(x, xo) < 1e-10
+
+
+def so_geom9(g):
+    g6 = g["geom6"]
+    idx = [[0, 1, 2], [1, 3, 4], [2, 4, 5]]
+    return g6[:, idx, :]
+
+
+def test_cg_edge_cases_and_verbose(capsys):
+    from sempy_b200.elliptic import elliptic_cg, elliptic_cg_loopy
+
+    g = load_golden("box008_N7")
+    m = golden_mesh(g)
+    x, it = elliptic_cg(m, np.zeros_like(g["b"]))  # early-out (elliptic.py:43)
+    assert it == 0 and not x.any()
+    x, it = elliptic_cg(m, g["b"], tol=1e-8, maxit=0)
+    assert it == 0 and not x.any()
+    x, it = elliptic_cg(m, g["b"], tol=1e-8, maxit=5)
+    assert it == 5
+    x, it = elliptic_cg(m, g["b"], tol=1e-8, maxit=3, verbose=1)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0].startswith("Initial rnorm=") and len(out) == 4 and out[1].startswith("niter=0 r0=") and " pap=" in out[3]
+    xl, itl = elliptic_cg_loopy(m, g["b"], tol=1e-8, maxit=10000)
+    assert itl == int(g["cg_niter_1e-08"]) or abs(itl - int(g["cg_niter_1e-08"])) <= 1
+    b = g["b"].copy()
+    elliptic_cg(m, b, tol=1e-8, maxit=10)
+    assert np.array_equal(b, g["b"])  # inputs are not mutated
+    with pytest.raises(ValueError):
+        elliptic_cg(m, g["b"][:-1])
+
+
+def test_device_tensors_and_operator():
+    torch = pytest.importorskip("torch")
+    from sempy_b200.elliptic import elliptic_ax, elliptic_cg
+    from sempy_b200.iterative import cg
+
+    g = load_golden("box008_N7")
+    m = golden_mesh(g)
+    p = torch.from_numpy(g["p"]).cuda()
+    ax = elliptic_ax(m, p)
+    assert ax.is_cuda and rel_inf(ax.cpu().numpy(), g["ax_raw"]) <= AX_TOL
+    x = torch.from_numpy(g["p"]).cuda()
+    m.dssum(x)
+    assert rel_inf(x.cpu().numpy() * g["rmult"], g["p_cont"]) < 1e-15
+    xb, it = elliptic_cg(m, torch.from_numpy(g["b"]).cuda(), tol=1e-8, maxit=10000)
+    assert xb.is_cuda and abs(it - int(g["cg_niter_1e-08"])) <= 1
+    # iterative.cg with the device operator: assembled, masked A on a continuous vector
+    A = m.operator(mask=True, assemble=True)
+    xg, itg = cg(A, g["b"], tol=1e-8, maxit=10000)
+    assert np.isfinite(xg).all() and itg > 0
+
+
+@pytest.mark.parametrize("dims,perturb,N", [((6, 6, 6), 0.0, 7), ((5, 4, 3), 0.3, 7), ((3, 3, 3), 0.3, 15), ((4, 3, 2), 0.3, 10), ((3, 2, 2), 0.25, 1), ((7, 5, 3), 0.2, 2), ((2, 2, 2), 0.3, 5)])
+def test_generated_meshes_vs_oracle(dims, perturb, N):
+    """Seeded inputs on generated boxes (straight and deformed, every kernel
+    family: Nq=8 tuned, Nq=16, generic) against the CPU oracle."""
+    from sempy_b200.elliptic import elliptic_ax, elliptic_cg, elliptic_pcg
+    from sempy_b200.mesh import box_mesh
+
+    m = box_mesh(*dims, perturb=perturb, seed=1)
+    m.find_physical_coordinates(N)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    E = m.get_num_elems()
+    D = np.ascontiguousarray(__import__("sempy_b200.derivative", fromlist=["x"]).reference_derivative_matrix(N))
+    geom = m.get_geom()
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal(E * m.Np)
+    ax_o = so.elliptic_ax_batched(geom, p, N, D)
+    assert rel_inf(elliptic_ax(m, p), ax_o) <= AX_TOL
+    g2l, gs = m.get_global_to_local_map()
+    x = p.copy()
+    m.dssum(x)
+    assert rel_inf(x, so.gather_scatter(p, g2l, gs)) < 1e-15
+    assert np.array_equal(m.get_rmult(), so.multiplicity_inverse(g2l, gs))
+    X, Y, Z = m.get_x(), m.get_y(), m.get_z()
+    b = 3 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z) * m.get_mass() * m.get_jaco()
+    b = m.apply_mask(m.dssum(b))
+    axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
+    xo, ito = so.elliptic_cg(axo, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-12, maxit=2000)
+    xg, itg = elliptic_cg(m, b, tol=1e-12, maxit=2000)
+    assert abs(itg - ito) <= 1 and rel_inf(xg, xo) < 1e-10
+    dinv = m.mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
+    xo, ito = so.elliptic_pcg_jacobi(axo, dinv, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-12, maxit=2000)
+    xg, itg = elliptic_pcg(m, b, tol=1e-12, maxit=2000)
+    assert abs(itg - ito) <= 1 and rel_inf(xg, xo) < 1e-10
+
+
+@pytest.fixture(scope="module")
+def big_mesh():
+    """BASELINE config 2 size: 32^3 elements, N=7 (16.8 M local nodes)."""
+    from sempy_b200.mesh import box_mesh
+
+    m = box_mesh(32, perturb=0.3, seed=0)
+    m.find_physical_coordinates(7)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    return m
+
+
+def test_full_size_properties(big_mesh):
+    """Size-independent properties at 32^3 N=7 on device tensors: unique node
+    count, symmetry, null space, gather-scatter idempotence, partition of
+    unity of rmult, manufactured solution."""
+    torch = pytest.importorskip("torch")
+    from sempy_b200.elliptic import elliptic_ax, elliptic_pcg
+
+    m = big_mesh
+    n = m.get_num_elems() * m.Np
+    assert m.global_start.size - 1 == 225 ** 3
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    v = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    au, av = elliptic_ax(m, u), elliptic_ax(m, v)
+    s1, s2 = torch.dot(v, au).item(), torch.dot(u, av).item()
+    assert abs(s1 - s2) <= 1e-12 * max(abs(s1), abs(s2))  # A = A^T element by element
+    assert torch.dot(u, au).item() > 0
+    lin = elliptic_ax(m, 2.0 * u - 3.0 * v)
+    assert (lin - (2.0 * au - 3.0 * av)).abs().max().item() <= 1e-12 * au.abs().max().item()
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    assert elliptic_ax(m, ones).abs().max().item() <= 1e-11 * au.abs().max().item()  # constants in the null space
+    rm = torch.from_numpy(m.get_rmult()).cuda()
+    w = u.clone()
+    m.dssum(w)
+    w2 = (w * rm).clone()
+    m.dssum(w2)
+    assert (w2 - w).abs().max().item() <= 1e-14 * w.abs().max().item()  # dssum(rmult * dssum(x)) = dssum(x)
+    assert abs(rm.sum().item() - 225 ** 3) < 1e-6  # sum of 1/multiplicity = number of unique nodes
+    X, Y, Z = (torch.from_numpy(a).cuda() for a in (m.get_x(), m.get_y(), m.get_z()))
+    exact = torch.sin(np.pi * X) * torch.sin(np.pi * Y) * torch.sin(np.pi * Z)
+    b = 3 * np.pi ** 2 * exact * torch.from_numpy(m.get_mass() * m.get_jaco()).cuda()
+    m.dssum(b)
+    m.apply_mask(b)
+    x, it = elliptic_pcg(m, b, tol=1e-10, maxit=2000)
+    assert 0 < it < 2000
+    assert (x - exact).abs().max().item() < 1e-6  # spectral accuracy on the deformed mesh
+    # result is continuous and zero on the boundary
+    xc = x.clone()
+    m.dssum(xc)
+    assert (xc * rm - x).abs().max().item() < 1e-12
+    xm = x.clone()
+    m.apply_mask(xm)
+    assert torch.equal(xm, x)
