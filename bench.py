@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A *step* is one Jacobi-PCG solve (tol 1e-8) of the 3-D Poisson problem on a
-deformed box mesh of 32^3 elements at N=7 (BASELINE config 2; 16.8 M local
+box mesh of 32^3 elements at N=7 (BASELINE config 2; 16.8 M local
 nodes per GPU), i.e. ~50 passes of the hot path (fused Ax + mask + local pAp,
 gather-scatter, fused vector updates).  ``value`` is local DOF x iterations per
 second with everything resident in HBM; ``e2e`` is the same solve called through
@@ -107,12 +107,17 @@ class ClockSampler:
         return out
 
 
-def build_problem(nel, perturb=0.3):
-    """Deformed box mesh of nel^3 elements at N=7 plus the manufactured RHS of
+def build_problem(nel, perturb=0.0, comm=None):
+    """Box mesh of nel^3 elements (deformed if perturb > 0) at N=7 plus the manufactured RHS of
     the reference's poisson.py:27-40.  Returns (mesh, b_host)."""
     from sempy_b200.mesh import box_mesh
 
-    m = box_mesh(nel, perturb=perturb, seed=0)
+    if comm is not None and comm.size > 1:
+        # weak scaling: nel^3 elements per GPU as z-slabs of a (2 nel) x (2 nel) x (nel/4 * ranks) box,
+        # which ends at the (2 nel)^3 cube on 8 GPUs (64^3 for nel = 32)
+        m = box_mesh(2 * nel, 2 * nel, (nel // 4) * comm.size, perturb=perturb, seed=0, comm=comm)
+    else:
+        m = box_mesh(nel, perturb=perturb, seed=0)
     m.find_physical_coordinates(N_ORDER)
     m.establish_global_numbering()
     m.calc_geometric_factors()
@@ -171,7 +176,7 @@ def run_reference(args):
         "value": val, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "3D Poisson, deformed box 32^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
+        "config": {"workload": "3D Poisson, straight box 32^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
                    "sample": f"{nel}^3 elements, {iters} PCG iterations per step"},
         "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": cores, "kind": "port",
                          "sample": f"oracle (NumPy restatement, batched matmul Ax, BLAS threads = host default) Jacobi-PCG, "
@@ -184,19 +189,38 @@ def run_reference(args):
 def run_ours(args):
     import torch
 
-    from sempy_b200 import _capi
+    from sempy_b200 import _capi, distributed
     from sempy_b200.elliptic import elliptic_ax, elliptic_pcg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU bench: see sempy_b200.distributed (not wired into bench.py yet)")
     torch.cuda.set_device(local_rank)
+    comm = None
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = distributed.TorchComm()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def over_ranks(v, op):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
     peak, peak_kind = measured_peaks()
     nel = args.nel
     t_setup = time.perf_counter()
-    mesh, b_host = build_problem(nel)
+    mesh, b_host = build_problem(nel, args.perturb, comm)
     t_setup = time.perf_counter() - t_setup
     dof = mesh.get_num_elems() * mesh.Np
     ctx = mesh._context()
@@ -218,23 +242,24 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------
     for _ in range(args.warmup):
         x_dev, niter = solve_dev()
-    torch.cuda.synchronize()
+    sync_all()
     _capi.check(lib.semb_profile_enable(ctx.handle, 1))
     _capi.check(lib.semb_profile_reset(ctx.handle))
     launches0 = lib.semb_launch_count(ctx.handle)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    sync_all()
     ev0.record()
     iters_total = 0
     for _ in range(args.steps):
         x_dev, niter = solve_dev()
         iters_total += niter
     ev1.record()
-    torch.cuda.synchronize()
+    sync_all()
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = over_ranks(ev0.elapsed_time(ev1), "MAX")
+    dof_all = over_ranks(dof, "SUM")
     launches = lib.semb_launch_count(ctx.handle) - launches0
     import ctypes as C
 
@@ -244,7 +269,7 @@ def run_ours(args):
         _capi.check(lib.semb_profile_get(ctx.handle, kid, C.byref(tot), C.byref(cnt)))
         kern[name] = (tot.value, cnt.value)
     _capi.check(lib.semb_profile_enable(ctx.handle, 0))
-    value = dof * iters_total / (ms_total * 1e-3) / 1e9
+    value = dof_all * iters_total / (ms_total * 1e-3) / 1e9
     ax_ms = kern["ax"][0] / max(kern["ax"][1], 1)
     ax_gbs = BYTES_AX * dof / (ax_ms * 1e-3) / 1e9
 
@@ -261,45 +286,72 @@ def run_ours(args):
     p_dev = x_dev.clone()
     for _ in range(3):
         w = _ax(mesh, p_dev, _capi.AX_MASK | _capi.AX_GS)
-    torch.cuda.synchronize()
+    sync_all()
     reps = 20
     ev0.record()
     for _ in range(reps):
         w = _ax(mesh, p_dev, _capi.AX_MASK | _capi.AX_GS)
     ev1.record()
-    torch.cuda.synchronize()
-    axgs_ms = ev0.elapsed_time(ev1) / reps
-    axgs_gdofs = dof / (axgs_ms * 1e-3) / 1e9
+    sync_all()
+    axgs_ms = over_ranks(ev0.elapsed_time(ev1), "MAX") / reps
+    axgs_gdofs = dof_all / (axgs_ms * 1e-3) / 1e9
     axgs_gbs = (BYTES_AX + BYTES_GS) * dof / (axgs_ms * 1e-3) / 1e9
 
     # ---- end-to-end arm: host buffers through the public API ----------------
     for _ in range(2):
         solve_host()
+    sync_all()
     t0 = time.perf_counter()
     e_iters = 0
     for _ in range(args.steps):
         _, it = solve_host()
         e_iters += it
-    e_s = time.perf_counter() - t0
-    e2e_val = dof * e_iters / e_s / 1e9
+    sync_all()
+    e_s = over_ranks(time.perf_counter() - t0, "MAX")
+    e2e_val = dof_all * e_iters / e_s / 1e9
     # sanity: same answer on both arms and a solved problem
     assert np.allclose(x_pin_np, x_dev.cpu().numpy(), rtol=0, atol=1e-12)
 
-    # ---- CPU baseline: the oracle on a bounded sample of the same workload ---
-    t_cpu0 = time.perf_counter()
-    prob = oracle_problem(10)
-    cpu_val, _ = time_oracle(prob, 5, 2, 1)
-    cpu_secs = time.perf_counter() - t_cpu0
+    if world > 1:
+        all_clocks = comm.allgather(clocks)
+        reasons = sorted({r for c in all_clocks for r in c.get("reasons", [])})
+        sm = [c["sm_mhz"] for c in all_clocks if c.get("sm_mhz")]
+        clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": reasons,
+                  "per_rank_sm_mhz": sm}
+    unique_local = int(mesh.global_start.size - 1)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the oracle on a bounded sample of the same workload (N = 1 only) ---
+    cpu_baseline = None
+    if world == 1:
+        t_cpu0 = time.perf_counter()
+        prob = oracle_problem(10)
+        cpu_val, _ = time_oracle(prob, 5, 2, 1)
+        cpu_secs = time.perf_counter() - t_cpu0
+        cpu_baseline = {"value": cpu_val, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "oracle (NumPy restatement, batched matmul Ax) Jacobi-PCG, 10^3 elements N=7, "
+                                  "5 iterations x 2 steps (%.0f s incl. set-up)" % cpu_secs}
+    if world == 1:
+        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {nel}^3 elements, N=7, "
+                    "Jacobi-PCG tol 1e-8 (BASELINE config 2)")
+    else:
+        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {2 * nel}x{2 * nel}x{(nel // 4) * world} "
+                    f"elements in z-slabs of {nel ** 3} elements per GPU, N=7, Jacobi-PCG tol 1e-8 "
+                    "(weak scaling of BASELINE config 2; the 8-GPU mesh is the 64^3 box of config 4)")
 
     line = {
         "metric": "FP64 Jacobi-PCG Poisson throughput, N=7 (local DOF x iterations / s)",
-        "value": value, "unit": "GDOF/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D Poisson, deformed box {nel}^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
-                   "elements": mesh.get_num_elems(), "local_dof": dof, "unique_dof": int(mesh.global_start.size - 1),
-                   "iterations_per_step": iters_total / args.steps, "cache": "inputs larger than L2 (G alone is %.0f MB)" % (48.0 * dof / 1e6),
-                   "parallelism": "1 GPU", "setup_s": t_setup},
+        "config": {"workload": workload,
+                   "elements_per_gpu": mesh.get_num_elems(), "local_dof_per_gpu": dof, "local_dof_total": int(dof_all),
+                   "unique_dof_rank0": unique_local,
+                   "iterations_per_step": iters_total / args.steps, "cache": "inputs larger than L2 (G alone is %.0f MB per GPU)" % (48.0 * dof / 1e6),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one z-slab of elements per GPU, NCCL halo exchange overlapped with interior Ax + all-reduced dots",
+                   "setup_s": t_setup},
         "cg_iters_per_s": iters_total / (ms_total * 1e-3),
         "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + BYTES_GS, "achieved_gbs": axgs_gbs,
                   "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
@@ -309,13 +361,15 @@ def run_ours(args):
         "kernels": {"ax": kernel_entry("ax", BYTES_AX), "gs": kernel_entry("gs", BYTES_GS),
                     "update": kernel_entry("update", BYTES_UPDATE_PCG), "direction": kernel_entry("direction", BYTES_DIR_PCG)},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * dof, "d2h_bytes_per_step": 8 * dof,
+        "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * int(dof_all), "d2h_bytes_per_step": 8 * int(dof_all),
                 "ms_per_step": e_s / args.steps * 1e3, "api": "sempy_b200.elliptic.elliptic_pcg(mesh, b_host) -> x_host"},
         "gpu_launches": int(launches),
-        "cpu_baseline": {"value": cpu_val, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "oracle (NumPy restatement, batched matmul Ax) Jacobi-PCG, 10^3 elements N=7, 5 iterations x 2 steps (%.0f s incl. set-up)" % cpu_secs},
     }
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -325,6 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2)")
+    ap.add_argument("--perturb", type=float, default=0.0, help="vertex displacement in units of h (0.3 = the deformed mesh of config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -53,7 +53,8 @@ int semb_device_count(void);
  * context holds the device-resident form of exactly that state. */
 int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq);
 int semb_destroy(semb_ctx* ctx);
-/* Run on this CUDA stream (cudaStream_t as void*); NULL = the context's own. */
+/* Run on this CUDA stream (cudaStream_t as void*); NULL = the context's own
+ * non-blocking stream.  For the legacy default stream pass cudaStreamLegacy (0x1). */
 int semb_set_stream(semb_ctx* ctx, void* cuda_stream);
 int semb_synchronize(semb_ctx* ctx);
 
@@ -121,6 +122,32 @@ int semb_cg(semb_ctx* ctx, const double* b, double* x, double tol, int maxit, in
 typedef int (*semb_apply_fn)(void* user, const double* d_in, double* d_out, int64_t n);
 int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_apply_fn Minv, void* Minv_user,
                     const double* b, double* x, double tol, int maxit, int mem, int* niter, double* history);
+
+/* ---- multi-GPU ----------------------------------------------------------
+ * One process and one context per GPU; the elements are split into one
+ * contiguous slab per rank (the reference is single-process: it hands gslib
+ * comm = 0, sempy/mesh.py:437, and never partitions).  Nodes on the slab
+ * interfaces have copies on several ranks: semb_gs / semb_ax(GS) / semb_cg
+ * complete their sums with a neighbour exchange over NCCL (overlapped with the
+ * interior elements inside semb_cg) and the CG dots with an all-reduce.
+ *   semb_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller
+ *     broadcasts it (torch.distributed, MPI, a file...).
+ *   semb_comm_init: collective over all ranks.
+ *   semb_set_halo: interface tables of this rank, built by the host-side
+ *     partitioner (sempy_b200/distributed.py).  Send entries are grouped by
+ *     neighbour in an order both sides share; entry t is the sum of the local
+ *     copies send_ids[send_start[t] .. send_start[t+1]).  The exchange buffer is
+ *     [send entries | entries received, same layout].  Interface node i gets
+ *     the sum of buffer slots src_off[src_start[i] .. src_start[i+1]) (listed in
+ *     ascending rank order on every rank, so all GPUs add in the same order)
+ *     written to its local copies copy_ids[copy_start[i] .. copy_start[i+1]).
+ *     Elements [0, n_if_elems) are the ones that touch the interface; they are
+ *     computed first so that the exchange overlaps the rest. */
+int semb_comm_unique_id(char* id128);
+int semb_comm_init(semb_ctx* ctx, int nranks, int rank, const char* id128);
+int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* nb_count, const int64_t* send_start,
+                  const int32_t* send_ids, int64_t n_if, const int64_t* src_start, const int32_t* src_off,
+                  const int64_t* copy_start, const int32_t* copy_ids, int64_t n_if_elems);
 
 /* ---- device memory helpers for callers without their own allocator ------ */
 int semb_malloc(int device, void** ptr, int64_t bytes);

@@ -59,6 +59,13 @@ SIGNATURES = {
         [C.c_int, C.c_int64, APPLY_FN, C.c_void_p, APPLY_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
          C.c_int, C.POINTER(C.c_int), C.c_void_p],
     ),
+    "semb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "semb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "semb_set_halo": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_int64],
+    ),
     "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
     "semb_free": (C.c_int, [C.c_int, C.c_void_p]),
     "semb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <stdint.h>
 
 #include <string>
@@ -20,6 +21,16 @@ void set_error(const std::string& msg);
       ::semb::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" +       \
                         __FILE__ + ":" + std::to_string(__LINE__) + ")");                    \
       return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define SEMB_NCCL(call)                                                                      \
+  do {                                                                                       \
+    ncclResult_t err__ = (call);                                                             \
+    if (err__ != ncclSuccess) {                                                              \
+      ::semb::set_error(std::string(#call) + ": " + ncclGetErrorString(err__) + " (" +       \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ")");                    \
+      return 3;                                                                              \
     }                                                                                        \
   } while (0)
 
@@ -125,6 +136,25 @@ struct semb_ctx {
   int64_t hist_cap = 0;
   double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,stage
   int* h_pinned = nullptr;  // pinned {done, niter}
+
+  // multi-GPU: NCCL communicator, interface ("halo") tables of this rank's element slab
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_if_done = nullptr, ev_gathered = nullptr, ev_exchanged = nullptr;
+  bool have_halo = false;
+  std::vector<int> nb_rank;        // neighbour ranks
+  std::vector<int64_t> nb_off;     // start of each neighbour's block in the send region (nneigh+1)
+  int64_t n_send = 0;              // entries sent (= received)
+  int64_t* send_start = nullptr;   // CSR over send entries -> local copies to sum
+  int32_t* send_ids = nullptr;
+  int64_t n_if = 0;                // interface nodes of this rank
+  int64_t* src_start = nullptr;    // CSR per interface node -> offsets into hbuf, ascending rank
+  int32_t* src_off = nullptr;
+  int64_t* copy_start = nullptr;   // CSR per interface node -> local copies
+  int32_t* copy_ids = nullptr;
+  double* hbuf = nullptr;          // [send region | receive region]
+  int64_t n_if_elems = 0;          // elements [0, n_if_elems) touch the interface
 
   semb::Profile prof;
   int64_t launch_count = 0;

@@ -59,11 +59,11 @@ static int bind_device(semb_ctx* c) {
 // ---- K1 dispatch -----------------------------------------------------------
 template <int NQ>
 static int launch_ax_generic(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
-                             const int* done) {
+                             const int* done, int64_t part_off) {
   const unsigned grid = (unsigned)(e1 - e0);
   const uint32_t* mb = c->maskbits;
 #define SEMB_LAUNCH_G(M, DT) \
-  ax_generic_kernel<NQ, M, DT><<<grid, NQ * NQ, 0, c->stream>>>(p, c->G6, ap, mb, c->partials, e0, e1, c->D, done)
+  ax_generic_kernel<NQ, M, DT><<<grid, NQ * NQ, 0, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, c->D, done)
   if (mask && dot) SEMB_LAUNCH_G(true, true);
   else if (mask) SEMB_LAUNCH_G(true, false);
   else if (dot) SEMB_LAUNCH_G(false, true);
@@ -80,7 +80,7 @@ static int64_t ax_num_partials(const semb_ctx* c, int64_t e0, int64_t e1) {
 }
 
 static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
-                     const int* done) {
+                     const int* done, int64_t part_off = 0) {
   if (e1 <= e0) return 0;
   ProfScope ps(c, SEMB_K_AX);
   c->launch_count++;
@@ -99,7 +99,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
       attr_done[c->device & 63] = true;
     }
 #define SEMB_LAUNCH_8(M, DT) \
-  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials, e0, e1, d8, done)
+  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, d8, done)
     if (mask && dot) SEMB_LAUNCH_8(true, true);
     else if (mask) SEMB_LAUNCH_8(true, false);
     else if (dot) SEMB_LAUNCH_8(false, true);
@@ -111,7 +111,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
   switch (c->Nq) {
 #define SEMB_CASE(Q) \
   case Q:            \
-    return launch_ax_generic<Q>(c, p, ap, mask, dot, e0, e1, done);
+    return launch_ax_generic<Q>(c, p, ap, mask, dot, e0, e1, done, part_off);
     SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(9) SEMB_CASE(10)
     SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
 #undef SEMB_CASE
@@ -124,14 +124,16 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 // ---- K2 dispatch -----------------------------------------------------------
 static int launch_gs(semb_ctx* c, double* x, const int* done) {
   ProfScope ps(c, SEMB_K_GS);
+  GsPlan plan{0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
-    if (k.nseg == 0) continue;
-    const int grid = vec_grid(k.nseg);
-    const int32_t* ids = c->gs_ids + k.off;
+    if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
+    else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
+    else if (k.len == 8) { plan.n8 = k.nseg; plan.off8 = k.off; }
+  }
+  const int64_t total = plan.n2 + plan.n4 + plan.n8;
+  if (total > 0) {
     c->launch_count++;
-    if (k.len == 2) gs_fixed_kernel<2><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
-    else if (k.len == 4) gs_fixed_kernel<4><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
-    else if (k.len == 8) gs_fixed_kernel<8><<<grid, VEC_NT, 0, c->stream>>>(x, ids, k.nseg, done);
+    gs_fixed_kernel<<<vec_grid(total), VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
     SEMB_CUDA(cudaGetLastError());
   }
   if (c->gs_var_nseg > 0) {
@@ -140,6 +142,49 @@ static int launch_gs(semb_ctx* c, double* x, const int* done) {
                                                                       c->gs_var_nseg, done);
     SEMB_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// ---- multi-GPU halo --------------------------------------------------------
+static int halo_gather(semb_ctx* c, const double* x, cudaStream_t st, const int* done) {
+  if (c->n_send == 0) return 0;
+  c->launch_count++;
+  halo_gather_kernel<<<vec_grid(c->n_send), VEC_NT, 0, st>>>(x, c->send_start, c->send_ids, c->n_send, c->hbuf, done);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+static int halo_exchange(semb_ctx* c, cudaStream_t st) {
+  if (c->nb_rank.empty()) return 0;
+  SEMB_NCCL(ncclGroupStart());
+  for (size_t q = 0; q < c->nb_rank.size(); ++q) {
+    const int64_t off = c->nb_off[q], cnt = c->nb_off[q + 1] - off;
+    SEMB_NCCL(ncclSend(c->hbuf + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
+    SEMB_NCCL(ncclRecv(c->hbuf + c->n_send + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
+  }
+  SEMB_NCCL(ncclGroupEnd());
+  return 0;
+}
+static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done) {
+  if (c->n_if == 0) return 0;
+  c->launch_count++;
+  halo_scatter_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->src_start, c->src_off, c->copy_start,
+                                                           c->copy_ids, c->n_if, done);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+// Complete gather-scatter of one vector on the context's stream (no overlap).
+static int gs_full(semb_ctx* c, double* x, const int* done) {
+  if (c->have_halo) {
+    SEMB_TRY(halo_gather(c, x, c->stream, done));
+    SEMB_TRY(halo_exchange(c, c->stream));
+  }
+  SEMB_TRY(launch_gs(c, x, done));
+  if (c->have_halo) SEMB_TRY(halo_scatter(c, x, c->stream, done));
+  return 0;
+}
+static int allreduce_sum(semb_ctx* c, double* dev, int count) {
+  if (c->comm == nullptr || c->nranks == 1) return 0;
+  SEMB_NCCL(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
 
@@ -185,16 +230,40 @@ static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
   return 0;
 }
 
+// rmult = 1 / gs(ones)   (sempy/mesh.py:440-442); across ranks when a halo is set
+static int build_rmult(semb_ctx* c) {
+  if (!c->rmult) SEMB_CUDA(cudaMalloc(&c->rmult, sizeof(double) * (size_t)c->n));
+  fill_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, 1.0, c->n);
+  SEMB_TRY(gs_full(c, c->rmult, nullptr));
+  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->n);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->vec[4]) {  // cached Jacobi diagonal is stale
+    cudaFree(c->vec[4]);
+    c->vec[4] = nullptr;
+  }
+  return 0;
+}
+
 static int build_jacobi(semb_ctx* c) {
   SEMB_TRY(ensure_vec(c, 4));
   double* d = c->vec[4];
   c->launch_count++;
   diag_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->G6, d, c->E, c->Nq, c->D);
   SEMB_CUDA(cudaGetLastError());
-  SEMB_TRY(launch_gs(c, d, nullptr));
+  SEMB_TRY(gs_full(c, d, nullptr));
   c->launch_count++;
   jacobi_invert_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(d, c->have_mask ? c->maskbits : nullptr, c->n);
   SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t count) {
+  cudaFree(*dst);
+  *dst = nullptr;
+  SEMB_CUDA(cudaMalloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
+  if (count) SEMB_CUDA(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -257,6 +326,18 @@ int semb_destroy(semb_ctx* c) {
     for (cudaEvent_t e : c->prof.start[k]) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof.stop[k]) cudaEventDestroy(e);
   }
+  cudaFree(c->send_start);
+  cudaFree(c->send_ids);
+  cudaFree(c->src_start);
+  cudaFree(c->src_off);
+  cudaFree(c->copy_start);
+  cudaFree(c->copy_ids);
+  cudaFree(c->hbuf);
+  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_if_done) cudaEventDestroy(c->ev_if_done);
+  if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
+  if (c->ev_exchanged) cudaEventDestroy(c->ev_exchanged);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
@@ -380,18 +461,7 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   SEMB_CUDA(cudaMalloc(&c->gs_var_start, sizeof(int32_t) * var_start.size()));
   SEMB_CUDA(cudaMemcpy(c->gs_var_start, var_start.data(), sizeof(int32_t) * var_start.size(), cudaMemcpyHostToDevice));
   c->have_gs = true;
-  // rmult = 1 / gs(ones)   (sempy/mesh.py:440-442)
-  if (!c->rmult) SEMB_CUDA(cudaMalloc(&c->rmult, sizeof(double) * (size_t)c->n));
-  fill_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, 1.0, c->n);
-  SEMB_TRY(launch_gs(c, c->rmult, nullptr));
-  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->n);
-  SEMB_CUDA(cudaGetLastError());
-  SEMB_CUDA(cudaStreamSynchronize(c->stream));
-  if (c->vec[4]) {  // cached Jacobi diagonal is stale
-    cudaFree(c->vec[4]);
-    c->vec[4] = nullptr;
-  }
-  return 0;
+  return build_rmult(c);
 }
 
 int semb_set_mask(semb_ctx* c, const int64_t* mask_ids, int64_t n_mask) {
@@ -443,7 +513,7 @@ int semb_ax(semb_ctx* c, const double* p, double* ap, int flags, int mem) {
   SEMB_TRY(stage_in(c, p, mem, c->n, in, true));
   SEMB_TRY(stage_in(c, ap, mem, c->n, out, false));
   SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, c->E, nullptr));
-  if (gs) SEMB_TRY(launch_gs(c, out.dev, nullptr));
+  if (gs) SEMB_TRY(gs_full(c, out.dev, nullptr));
   SEMB_TRY(stage_out(c, ap, mem, c->n, out));
   return 0;
 }
@@ -454,7 +524,7 @@ int semb_gs(semb_ctx* c, double* x, int mem) {
   SEMB_TRY(bind_device(c));
   Staged v;
   SEMB_TRY(stage_in(c, x, mem, c->n, v, true));
-  SEMB_TRY(launch_gs(c, v.dev, nullptr));
+  SEMB_TRY(gs_full(c, v.dev, nullptr));
   SEMB_TRY(stage_out(c, x, mem, c->n, v));
   return 0;
 }
@@ -488,6 +558,7 @@ int semb_dot(semb_ctx* c, const double* x, const double* y, int weighted, double
   SEMB_CUDA(cudaGetLastError());
   double* scratch = reinterpret_cast<double*>(c->scal + 1);
   SEMB_TRY(reduce_partials(c, grid, 0, 1, scratch, nullptr));
+  SEMB_TRY(allreduce_sum(c, scratch, 1));
   SEMB_CUDA(cudaMemcpyAsync(out, scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
@@ -650,6 +721,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   else cg_init_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(bdev, xdev, r, p, c->rmult, nullptr, n, c->partials);
   SEMB_CUDA(cudaGetLastError());
   SEMB_TRY(reduce_partials(c, grid, grid, jac ? 2 : 1, two, nullptr));
+  SEMB_TRY(allreduce_sum(c, two, jac ? 2 : 1));
   cg_init_scalars_kernel<<<1, 1, 0, c->stream>>>(s, two, tol, maxit, jac ? 1 : 0);
   SEMB_CUDA(cudaGetLastError());
 
@@ -663,10 +735,30 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
     const int todo = std::min(chunk, maxit - issued);
     for (int it = 0; it < todo; ++it) {
       // Ap = mask(A p), local pAp partials      (elliptic.py:48-51)
-      SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
-      SEMB_TRY(reduce_partials(c, ax_num_partials(c, 0, c->E), 0, 1, &s->pAp, done));
       // Ap = dssum(Ap)                          (elliptic.py:54)
-      SEMB_TRY(launch_gs(c, Ap, done));
+      if (c->have_halo) {
+        // slab interface first; its partial sums travel to the neighbours while the interior runs
+        const int64_t nif = c->n_if_elems;
+        const int64_t np1 = ax_num_partials(c, 0, nif);
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, nif, done, 0));
+        SEMB_CUDA(cudaEventRecord(c->ev_if_done, c->stream));
+        SEMB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_if_done, 0));
+        SEMB_TRY(halo_gather(c, Ap, c->comm_stream, done));
+        SEMB_CUDA(cudaEventRecord(c->ev_gathered, c->comm_stream));
+        SEMB_TRY(halo_exchange(c, c->comm_stream));
+        SEMB_CUDA(cudaEventRecord(c->ev_exchanged, c->comm_stream));
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, nif, c->E, done, np1));
+        SEMB_TRY(reduce_partials(c, np1 + ax_num_partials(c, nif, c->E), 0, 1, &s->pAp, done));
+        SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
+        SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
+        SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
+        SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
+      } else {
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
+        SEMB_TRY(reduce_partials(c, ax_num_partials(c, 0, c->E), 0, 1, &s->pAp, done));
+        SEMB_TRY(launch_gs(c, Ap, done));
+      }
       // x, r, rdotr                             (elliptic.py:56-60)
       {
         ProfScope ps(c, SEMB_K_UPDATE);
@@ -676,6 +768,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_CUDA(cudaGetLastError());
       }
       SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
+      SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
       c->launch_count++;
       cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
       SEMB_CUDA(cudaGetLastError());
@@ -783,6 +876,66 @@ int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_a
   if (mem == SEMB_HOST) SEMB_CUDA(cudaMemcpy(x, xdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
   SEMB_CUDA(cudaDeviceSynchronize());
   return 0;
+}
+
+// ---- multi-GPU -------------------------------------------------------------
+int semb_comm_unique_id(char* id128) {
+  SEMB_CHECK(id128 != nullptr, "semb_comm_unique_id: NULL argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  SEMB_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int semb_comm_init(semb_ctx* c, int nranks, int rank, const char* id128) {
+  SEMB_CHECK(c && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "semb_comm_init: bad argument");
+  SEMB_CHECK(c->comm == nullptr, "semb_comm_init: communicator already set");
+  SEMB_TRY(bind_device(c));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  SEMB_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+  c->nranks = nranks;
+  c->rank = rank;
+  SEMB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_if_done, cudaEventDisableTiming));
+  SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
+  SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_exchanged, cudaEventDisableTiming));
+  return 0;
+}
+
+int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb_count, const int64_t* send_start,
+                  const int32_t* send_ids, int64_t n_if, const int64_t* src_start, const int32_t* src_off,
+                  const int64_t* copy_start, const int32_t* copy_ids, int64_t n_if_elems) {
+  SEMB_CHECK(c != nullptr && nneigh >= 0 && n_if >= 0, "semb_set_halo: bad argument");
+  SEMB_CHECK(c->have_gs, "semb_set_halo: call semb_set_gather_scatter first");
+  SEMB_CHECK(nneigh == 0 || c->comm != nullptr, "semb_set_halo: call semb_comm_init first");
+  SEMB_CHECK(n_if_elems >= 0 && n_if_elems <= c->E, "semb_set_halo: n_if_elems out of range");
+  SEMB_TRY(bind_device(c));
+  c->nb_rank.assign(nb_rank, nb_rank + nneigh);
+  c->nb_off.assign(1, 0);
+  for (int q = 0; q < nneigh; ++q) {
+    SEMB_CHECK(nb_rank[q] >= 0 && nb_rank[q] < c->nranks && nb_rank[q] != c->rank && nb_count[q] > 0,
+               "semb_set_halo: bad neighbour entry");
+    c->nb_off.push_back(c->nb_off.back() + nb_count[q]);
+  }
+  c->n_send = c->nb_off.back();
+  c->n_if = n_if;
+  c->n_if_elems = n_if_elems;
+  if (c->n_send > 0) {
+    SEMB_CHECK(send_start && send_ids && src_start && src_off && copy_start && copy_ids, "semb_set_halo: NULL table");
+    SEMB_TRY(upload(&c->send_start, send_start, (size_t)c->n_send + 1));
+    SEMB_TRY(upload(&c->send_ids, send_ids, (size_t)send_start[c->n_send]));
+    SEMB_TRY(upload(&c->src_start, src_start, (size_t)n_if + 1));
+    SEMB_TRY(upload(&c->src_off, src_off, (size_t)src_start[n_if]));
+    SEMB_TRY(upload(&c->copy_start, copy_start, (size_t)n_if + 1));
+    SEMB_TRY(upload(&c->copy_ids, copy_ids, (size_t)copy_start[n_if]));
+    cudaFree(c->hbuf);
+    c->hbuf = nullptr;
+    SEMB_CUDA(cudaMalloc(&c->hbuf, sizeof(double) * 2 * (size_t)c->n_send));
+  }
+  c->have_halo = c->nranks > 1;
+  return build_rmult(c);  // multiplicities now count the copies on the other ranks too
 }
 
 // ---- memory helpers --------------------------------------------------------

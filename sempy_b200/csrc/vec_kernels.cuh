@@ -19,33 +19,50 @@ constexpr int VEC_NT = 256;
 // back to every copy.  Traffic: 8 + 4 + 8 bytes per shared local node.
 // ---------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(VEC_NT)
-gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t nseg, const int* __restrict__ done) {
-  if (done != nullptr && *done) return;
-  for (int64_t s = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * VEC_NT) {
-    int id[L];
-    if (L == 2) {
-      const int2 v = __ldg(reinterpret_cast<const int2*>(ids) + s);
-      id[0] = v.x;
-      id[1] = v.y;
-    } else {
+__device__ __forceinline__ void gs_segment(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t s) {
+  int id[L];
+  if (L == 2) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(ids) + s);
+    id[0] = v.x;
+    id[1] = v.y;
+  } else {
 #pragma unroll
-      for (int c = 0; c < L / 4; ++c) {
-        const int4 v = __ldg(reinterpret_cast<const int4*>(ids) + s * (L / 4) + c);
-        id[4 * c] = v.x;
-        id[4 * c + 1] = v.y;
-        id[4 * c + 2] = v.z;
-        id[4 * c + 3] = v.w;
-      }
+    for (int c = 0; c < L / 4; ++c) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(ids) + s * (L / 4) + c);
+      id[4 * c] = v.x;
+      id[4 * c + 1] = v.y;
+      id[4 * c + 2] = v.z;
+      id[4 * c + 3] = v.w;
     }
-    double v[L];
+  }
+  double v[L];
 #pragma unroll
-    for (int c = 0; c < L; ++c) v[c] = x[id[c]];
-    double sum = v[0];
+  for (int c = 0; c < L; ++c) v[c] = x[id[c]];
+  double sum = v[0];
 #pragma unroll
-    for (int c = 1; c < L; ++c) sum += v[c];
+  for (int c = 1; c < L; ++c) sum += v[c];
 #pragma unroll
-    for (int c = 0; c < L; ++c) x[id[c]] = sum;
+  for (int c = 0; c < L; ++c) x[id[c]] = sum;
+}
+
+// All fixed-length classes in ONE launch: thread t owns segment t of the
+// concatenation [len-2 | len-4 | len-8]; only the warps that straddle a class
+// boundary diverge.  (Three launches cost two extra drain/launch bubbles and a
+// nearly empty len-8 grid: 8.8 us for 0.13 waves, profiles/r01_ncu_summary.md.)
+struct GsPlan {
+  int64_t n2, n4, n8;       // segments per class
+  int64_t off2, off4, off8; // start of each class in ids (multiples of 4 ints)
+};
+
+__global__ void __launch_bounds__(VEC_NT)
+gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
+                const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  const int64_t total = plan.n2 + plan.n4 + plan.n8;
+  for (int64_t t = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * VEC_NT) {
+    if (t < plan.n2) gs_segment<2>(x, ids + plan.off2, t);
+    else if (t < plan.n2 + plan.n4) gs_segment<4>(x, ids + plan.off4, t - plan.n2);
+    else gs_segment<8>(x, ids + plan.off8, t - plan.n2 - plan.n4);
   }
 }
 
@@ -59,6 +76,40 @@ gs_var_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const int
     double sum = 0.0;
     for (int q = lo; q < hi; ++q) sum += x[ids[q]];
     for (int q = lo; q < hi; ++q) x[ids[q]] = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU part of the gather-scatter (elements are split into one slab per
+// GPU; nodes on the slab interfaces have copies on more than one rank).
+//   halo_gather : hbuf[t] = sum of this rank's copies of send entry t
+//   (NCCL send/recv of the send region into the neighbours' receive regions)
+//   halo_scatter: every copy of interface node i <- sum over the sharing ranks,
+//                 added in ascending rank order on every rank (bitwise equal
+//                 copies on all GPUs).
+// Takes over what gslib's pairwise exchange would do under MPI (the reference
+// passes comm = 0 and never runs it, sempy/mesh.py:437).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_NT)
+halo_gather_kernel(const double* __restrict__ x, const int64_t* __restrict__ start, const int32_t* __restrict__ ids,
+                   int64_t nent, double* __restrict__ hbuf, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  for (int64_t t = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; t < nent; t += (int64_t)gridDim.x * VEC_NT) {
+    double s = 0.0;
+    for (int64_t q = start[t]; q < start[t + 1]; ++q) s += x[ids[q]];
+    hbuf[t] = s;
+  }
+}
+
+__global__ void __launch_bounds__(VEC_NT)
+halo_scatter_kernel(double* __restrict__ x, const double* __restrict__ hbuf, const int64_t* __restrict__ src_start,
+                    const int32_t* __restrict__ src_off, const int64_t* __restrict__ copy_start,
+                    const int32_t* __restrict__ copy_ids, int64_t n_if, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  for (int64_t i = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; i < n_if; i += (int64_t)gridDim.x * VEC_NT) {
+    double s = 0.0;
+    for (int64_t q = src_start[i]; q < src_start[i + 1]; ++q) s += hbuf[src_off[q]];
+    for (int64_t q = copy_start[i]; q < copy_start[i + 1]; ++q) x[copy_ids[q]] = s;
   }
 }
 

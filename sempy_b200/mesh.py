@@ -25,7 +25,7 @@ import os
 
 import numpy as np
 
-from sempy_b200 import _capi
+from sempy_b200 import _capi, distributed
 from sempy_b200.derivative import reference_derivative_matrix
 from sempy_b200.gradient import gradient
 from sempy_b200.interpolation import lagrange
@@ -129,13 +129,16 @@ def global_numbering_from_coordinates(xe, ye, ze, tol=1e-12):
     return ids.reshape(E, Np), order, start
 
 
-def bounding_box_mask(xe, ye, ze, tol=1e-8):
+def bounding_box_mask(xe, ye, ze, tol=1e-8, bbox=None):
     """0 where any coordinate is within ``tol`` of the global bounding box
-    (homogeneous Dirichlet), else 1; sempy/mesh.py:449-477, flat (E*Np,)."""
+    (homogeneous Dirichlet), else 1; sempy/mesh.py:449-477, flat (E*Np,).
+    ``bbox`` = ((xmin, xmax), (ymin, ymax), (zmin, zmax)) overrides the local
+    extrema (multi-GPU: the box of the whole mesh)."""
     mask = np.ones(xe.shape)
-    for c in (xe, ye, ze):
-        mask[np.abs(c - np.min(c)) < tol] = 0
-        mask[np.abs(c - np.max(c)) < tol] = 0
+    for axis, c in enumerate((xe, ye, ze)):
+        lo, hi = (np.min(c), np.max(c)) if bbox is None else bbox[axis]
+        mask[np.abs(c - lo) < tol] = 0
+        mask[np.abs(c - hi) < tol] = 0
     return mask.reshape(-1)
 
 
@@ -160,19 +163,23 @@ class _Context:
 
 
 class Mesh:
-    def __init__(self, fname, debug=0):
+    def __init__(self, fname, debug=0, comm=None):
         if not isinstance(fname, str):
             raise Exception("Only strings are allowed for file name")
         self.debug = debug
+        self.comm = comm if comm is not None else distributed.SerialComm()
         self._reset_device_state()
         self.read(fname)
 
     # -- construction -------------------------------------------------------
     @classmethod
-    def from_arrays(cls, points, hexes, debug=0):
-        """Build from vertex coordinates (nv,3) and hexahedra (E,8) in gmsh order."""
+    def from_arrays(cls, points, hexes, debug=0, comm=None):
+        """Build from vertex coordinates (nv,3) and hexahedra (E,8) in gmsh order.
+        With a multi-rank ``comm`` every rank passes the WHOLE mesh and keeps
+        its own contiguous slab of elements (see sempy_b200/distributed.py)."""
         self = cls.__new__(cls)
         self.debug = debug
+        self.comm = comm if comm is not None else distributed.SerialComm()
         self._reset_device_state()
         self._set_topology(np.asarray(points, dtype=np.float64), np.asarray(hexes, dtype=np.int64))
         return self
@@ -194,6 +201,22 @@ class Mesh:
 
     def _set_topology(self, points, hexes):
         assert len(hexes) > 0 and len(points) > 0
+        self.num_global_elements = hexes.shape[0]
+        self._halo = None
+        self._shared_vertex = None
+        self._n_if_elems = 0
+        if self.comm.size > 1:
+            # this rank's slab, interface elements first so that their Ax can be launched ahead
+            ranges = distributed.slab_ranges(hexes.shape[0], self.comm.size)
+            lo, hi = ranges[self.comm.rank]
+            if hi <= lo:
+                raise Exception("more ranks than elements")
+            self._shared_vertex = distributed.shared_vertex_flags(hexes, ranges, len(points))
+            order, self._n_if_elems = distributed.interface_first_order(hexes[lo:hi], self._shared_vertex)
+            self.elem_global = lo + order
+            hexes = hexes[self.elem_global]
+        else:
+            self.elem_global = np.arange(hexes.shape[0])
         self.elem_to_vert_map = hexes
         self.num_elements = hexes.shape[0]
         self.num_verts = hexes.shape[1]
@@ -296,13 +319,23 @@ class Mesh:
         self.global_id, self.global_to_local, self.global_start = global_numbering_from_coordinates(
             self.xe, self.ye, self.ze
         )
+        if self.comm.size > 1:
+            # ids are local to the rank; nodes with copies on other ranks go into the halo tables
+            cand = distributed.candidate_node_mask(self.elem_to_vert_map, self._shared_vertex, self.N)
+            self._halo = distributed.build_halo(self.comm, self.xe, self.ye, self.ze, cand, self.global_id,
+                                                self.global_to_local, self.global_start,
+                                                global_numbering_from_coordinates)
         self._dirty["gs"] = True
         self.rmult = np.empty(self.num_elements * self.Np, dtype=np.float64)
         ctx = self._context(need=("gs",))
         _capi.check(ctx.lib.semb_get_rmult(ctx.handle, self.rmult.ctypes.data, _capi.HOST))
 
     def setup_mask(self):
-        self.mask = bounding_box_mask(self.xe, self.ye, self.ze)
+        bbox = None
+        if self.comm.size > 1:
+            ext = self.comm.allgather([(float(c.min()), float(c.max())) for c in (self.xe, self.ye, self.ze)])
+            bbox = [(min(e[a][0] for e in ext), max(e[a][1] for e in ext)) for a in range(3)]
+        self.mask = bounding_box_mask(self.xe, self.ye, self.ze, bbox=bbox)
         self._dirty["mask"] = True
 
     # -- device context ---------------------------------------------------------
@@ -328,6 +361,8 @@ class Mesh:
                 g2l = np.ascontiguousarray(self.global_to_local, dtype=np.int64)
                 gst = np.ascontiguousarray(self.global_start, dtype=np.int64)
                 _capi.check(lib.semb_set_gather_scatter(ctx.handle, g2l.ctypes.data, gst.ctypes.data, gst.size - 1))
+                if self.comm.size > 1:
+                    self._attach_halo(ctx)
             elif key == "mask":
                 if self.mask is None:
                     raise RuntimeError("call setup_mask() first")
@@ -335,6 +370,23 @@ class Mesh:
                 _capi.check(lib.semb_set_mask(ctx.handle, ids.ctypes.data, ids.size))
             self._dirty[key] = False
         return ctx
+
+    def _attach_halo(self, ctx):
+        """NCCL communicator (once per context) and this rank's interface tables."""
+        lib = ctx.lib
+        if not getattr(ctx, "comm_ready", False):
+            uid = C.create_string_buffer(128)
+            if self.comm.rank == 0:
+                _capi.check(lib.semb_comm_unique_id(uid))
+            raw = self.comm.bcast(bytes(uid.raw), root=0)
+            _capi.check(lib.semb_comm_init(ctx.handle, self.comm.size, self.comm.rank, raw))
+            ctx.comm_ready = True
+        h = self._halo
+        keep = [np.ascontiguousarray(h[k]) for k in ("nb_rank", "nb_count", "send_start", "send_ids", "src_start",
+                                                      "src_off", "copy_start", "copy_ids")]
+        _capi.check(lib.semb_set_halo(ctx.handle, keep[0].size, keep[0].ctypes.data, keep[1].ctypes.data,
+                                      keep[2].ctypes.data, keep[3].ctypes.data, h["n_if"], keep[4].ctypes.data,
+                                      keep[5].ctypes.data, keep[6].ctypes.data, keep[7].ctypes.data, self._n_if_elems))
 
     def _vector_args(self, x, name):
         """(pointer, mem flag, keep-alive) for an in-place vector argument."""
@@ -353,7 +405,10 @@ class Mesh:
         if mem == _capi.DEVICE:
             import torch
 
-            _capi.check(ctx.lib.semb_set_stream(ctx.handle, torch.cuda.current_stream().cuda_stream))
+            # torch's default stream has handle 0, which semb_set_stream reads as "the context's own
+            # stream": name the legacy default stream explicitly (cudaStreamLegacy == 0x1).
+            handle = torch.cuda.current_stream().cuda_stream
+            _capi.check(ctx.lib.semb_set_stream(ctx.handle, handle if handle else 1))
         else:
             _capi.check(ctx.lib.semb_set_stream(ctx.handle, None))
 
@@ -432,6 +487,6 @@ def load_mesh(fname):
     return Mesh(os.path.join(dir_path, "meshes", fname))
 
 
-def box_mesh(nx, ny=None, nz=None, perturb=0.0, seed=0):
+def box_mesh(nx, ny=None, nz=None, perturb=0.0, seed=0, comm=None):
     """Synthetic box mesh without a file round trip."""
-    return Mesh.from_arrays(*box_mesh_arrays(nx, ny, nz, perturb, seed))
+    return Mesh.from_arrays(*box_mesh_arrays(nx, ny, nz, perturb, seed), comm=comm)

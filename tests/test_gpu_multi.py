@@ -1,0 +1,104 @@
+"""Two-rank GPU test of the multi-GPU path (NCCL halo exchange + all-reduced
+dots): results on the partitioned mesh against the CPU oracle on the whole
+mesh.  Needs two devices (`gpurun --gpus 2`); skipped otherwise."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    from sempy_b200 import _capi
+
+    return _capi.lib().semb_device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, size, port, dims, perturb, N, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["SEMB_DEVICE"] = str(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from oracle import sem_oracle as so
+        from sempy_b200 import _capi
+        from sempy_b200 import distributed as dd
+        from sempy_b200 import mesh as pm
+        from sempy_b200.derivative import reference_derivative_matrix
+        from sempy_b200.elliptic import _ax, elliptic_cg, elliptic_pcg
+
+        comm = dd.TorchComm()
+        pts, hexes = pm.box_mesh_arrays(*dims, perturb=perturb, seed=2)
+        m = pm.Mesh.from_arrays(pts, hexes, comm=comm)
+        m.find_physical_coordinates(N)
+        m.establish_global_numbering()
+        m.calc_geometric_factors()
+        m.setup_mask()
+        E, Np = len(hexes), m.Np
+        take = lambda v: v.reshape(E, Np)[m.elem_global].reshape(-1)
+        # the whole mesh on the CPU oracle
+        D = np.ascontiguousarray(reference_derivative_matrix(N))
+        gx, gy, gz = so.physical_coordinates(*so.element_vertices(pts, hexes), N)
+        _, g2l, gs = so.global_numbering(gx, gy, gz)
+        geom, jaco, mass = so.geometric_factors(gx, gy, gz, N)
+        rmult, mask = so.multiplicity_inverse(g2l, gs), so.dirichlet_mask(gx, gy, gz)
+        rng = np.random.default_rng(4)
+        p = so.gather_scatter(rng.standard_normal(E * Np), g2l, gs) * rmult
+        errs = {}
+        errs["rmult"] = float(np.abs(m.get_rmult() - take(rmult)).max())
+        errs["mask"] = float(np.abs(m.mask - take(mask)).max())
+        x = take(p * 1.7).copy()
+        m.dssum(x)
+        ref = take(so.gather_scatter(p * 1.7, g2l, gs))
+        errs["dssum"] = float(np.abs(x - ref).max() / np.abs(ref).max())
+        full = _ax(m, take(p), _capi.AX_MASK | _capi.AX_GS)
+        ref = take(so.gather_scatter(so.elliptic_ax_batched(geom, p, N, D) * mask, g2l, gs))
+        errs["ax_full"] = float(np.abs(full - ref).max() / np.abs(ref).max())
+        b = 3 * np.pi ** 2 * np.sin(np.pi * gx) * np.sin(np.pi * gy) * np.sin(np.pi * gz) * mass * jaco
+        b = so.gather_scatter(b.reshape(-1), g2l, gs) * mask
+        axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
+        xo, ito = so.elliptic_cg(axo, mask, g2l, gs, rmult, b, tol=1e-12, maxit=3000)
+        xg, itg = elliptic_cg(m, take(b), tol=1e-12, maxit=3000)
+        errs["cg_iters"] = float(abs(itg - ito))
+        errs["cg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
+        dinv = mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
+        xo, ito = so.elliptic_pcg_jacobi(axo, dinv, mask, g2l, gs, rmult, b, tol=1e-12, maxit=3000)
+        xg, itg = elliptic_pcg(m, take(b), tol=1e-12, maxit=3000)
+        errs["pcg_iters"] = float(abs(itg - ito))
+        errs["pcg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
+        res = comm.allgather(errs)
+        if rank == 0:
+            import json
+
+            with open(out, "w") as fh:
+                json.dump(res, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims,perturb,N", [((3, 3, 4), 0.3, 7), ((4, 3, 5), 0.2, 4)])
+def test_two_rank_solver_matches_oracle(dims, perturb, N, tmp_path):
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "res.json")
+    mp.spawn(_worker, args=(2, _free_port(), dims, perturb, N, out), nprocs=2, join=True)
+    for e in json.load(open(out)):
+        assert e["rmult"] == 0.0 and e["mask"] == 0.0
+        assert e["dssum"] < 1e-15 and e["ax_full"] <= 1e-12
+        assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
+        assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
