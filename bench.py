@@ -243,7 +243,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         x_dev, niter = solve_dev()
     sync_all()
-    _capi.check(lib.semb_profile_enable(ctx.handle, 1))
+    # inside the timed region only the dominant kernel (the fused Ax) is bracketed by events;
+    # the other kernels are timed in a second, untimed pass below (every bracket costs two event records)
+    _capi.check(lib.semb_profile_enable(ctx.handle, 1 | ((1 << _capi.K_AX) << 1)))
     _capi.check(lib.semb_profile_reset(ctx.handle))
     launches0 = lib.semb_launch_count(ctx.handle)
     sampler = ClockSampler(local_rank)
@@ -263,22 +265,35 @@ def run_ours(args):
     launches = lib.semb_launch_count(ctx.handle) - launches0
     import ctypes as C
 
-    kern = {}
-    for name, kid in (("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE), ("direction", _capi.K_DIRECTION)):
-        tot, cnt = C.c_double(0), C.c_int64(0)
-        _capi.check(lib.semb_profile_get(ctx.handle, kid, C.byref(tot), C.byref(cnt)))
-        kern[name] = (tot.value, cnt.value)
+    def read_profile(names):
+        out = {}
+        for name, kid in names:
+            tot, cnt = C.c_double(0), C.c_int64(0)
+            _capi.check(lib.semb_profile_get(ctx.handle, kid, C.byref(tot), C.byref(cnt)))
+            out[name] = (tot.value, cnt.value)
+        return out
+
+    kern = read_profile([("ax", _capi.K_AX)])
+    # second pass (not part of `value`): all four kernel kinds bracketed
+    _capi.check(lib.semb_profile_enable(ctx.handle, 1))
+    _capi.check(lib.semb_profile_reset(ctx.handle))
+    ev0.record()
+    solve_dev()
+    ev1.record()
+    sync_all()
+    ms_pass2 = ev0.elapsed_time(ev1)
+    kern2 = read_profile([("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE), ("direction", _capi.K_DIRECTION)])
     _capi.check(lib.semb_profile_enable(ctx.handle, 0))
     value = dof_all * iters_total / (ms_total * 1e-3) / 1e9
     ax_ms = kern["ax"][0] / max(kern["ax"][1], 1)
     ax_gbs = BYTES_AX * dof / (ax_ms * 1e-3) / 1e9
 
     def kernel_entry(name, bytes_per_dof):
-        tot, cnt = kern[name]
+        tot, cnt = kern2[name]
         ms = tot / max(cnt, 1)
         gbs = bytes_per_dof * dof / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"ms": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs, "frac": gbs / peak,
-                "share_of_step": tot / ms_total}
+                "share_of_step": tot / ms_pass2}
 
     # ---- fused Ax + mask + gather-scatter alone (the north-star 70 % target) ----
     from sempy_b200.elliptic import _ax
@@ -357,7 +372,8 @@ def run_ours(args):
                   "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
         "roofline": {"bound": "hbm", "kernel": "ax8_kernel (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
                      "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak, "traffic": None,
-                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
+                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "launches_timed": kern["ax"][1],
+                     "share_of_step": kern["ax"][0] / ms_total, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
         "kernels": {"ax": kernel_entry("ax", BYTES_AX), "gs": kernel_entry("gs", BYTES_GS),
                     "update": kernel_entry("update", BYTES_UPDATE_PCG), "direction": kernel_entry("direction", BYTES_DIR_PCG)},
         "clocks": clocks,

@@ -157,7 +157,9 @@ int semb_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind 
 /* ---- measurement --------------------------------------------------------
  * With profiling on, every launch of the named kernels is bracketed by CUDA
  * events on the context's stream; semb_profile_get returns the summed device
- * time and the launch count since the last reset. */
+ * time and the launch count since the last reset.  on = 1 brackets every
+ * kernel kind; on = 1 | (mask << 1) only the kinds whose bit (1 << SEMB_K_*) is
+ * set in mask (each bracket costs two event records on the stream). */
 int semb_profile_enable(semb_ctx* ctx, int on);
 int semb_profile_reset(semb_ctx* ctx);
 int semb_profile_get(semb_ctx* ctx, int kernel, double* total_ms, int64_t* launches);

@@ -5,5 +5,5 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libsemb200.so"
 NVCC="${NVCC:-nvcc}"
 "$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-  -Xcompiler -fPIC -shared -o "$OUT" "$HERE/semb200.cu" -lnccl "$@"
+  -Xcompiler -fPIC -shared -o "$OUT" "$HERE/semb200.cu" -ldl "$@"
 echo "built $OUT"

@@ -24,11 +24,33 @@ void set_error(const std::string& msg);
     }                                                                                        \
   } while (0)
 
+// NCCL is bound at run time (dlopen), not at link time: a process that also
+// imports torch must end up with ONE libnccl.so.2 -- torch's bundled one when
+// torch is loaded, the system one otherwise.  Linking -lnccl would pull the
+// system library in first and break a later `import torch`.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+const NcclApi& nccl();  // loads on first use; ok == false if no NCCL library could be bound
+
 #define SEMB_NCCL(call)                                                                      \
   do {                                                                                       \
-    ncclResult_t err__ = (call);                                                             \
+    if (!::semb::nccl().ok) {                                                                \
+      ::semb::set_error("NCCL library (libnccl.so.2) could not be loaded");                  \
+      return 3;                                                                              \
+    }                                                                                        \
+    ncclResult_t err__ = ::semb::nccl().call;                                                \
     if (err__ != ncclSuccess) {                                                              \
-      ::semb::set_error(std::string(#call) + ": " + ncclGetErrorString(err__) + " (" +       \
+      ::semb::set_error(std::string("nccl" #call) + ": " + ::semb::nccl().GetErrorString(err__) + " (" + \
                         __FILE__ + ":" + std::to_string(__LINE__) + ")");                    \
       return 3;                                                                              \
     }                                                                                        \
@@ -89,6 +111,7 @@ struct GsClass {
 
 struct Profile {
   bool on = false;
+  int mask = 0xffff;
   std::vector<cudaEvent_t> start[SEMB_K_COUNT], stop[SEMB_K_COUNT];
   size_t used[SEMB_K_COUNT] = {0, 0, 0, 0};
   double total_ms[SEMB_K_COUNT] = {0, 0, 0, 0};

@@ -1,4 +1,6 @@
 // libsemb200: C ABI (include/semb200.h) over the sm_100a kernels.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -12,6 +14,32 @@ namespace semb {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+const NcclApi& nccl() {
+  static NcclApi api = [] {
+    NcclApi a;
+    // an already loaded libnccl.so.2 (torch's) wins; otherwise load whatever the system provides
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+#define SEMB_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
+    SEMB_SYM(GetUniqueId, "ncclGetUniqueId");
+    SEMB_SYM(CommInitRank, "ncclCommInitRank");
+    SEMB_SYM(CommDestroy, "ncclCommDestroy");
+    SEMB_SYM(GroupStart, "ncclGroupStart");
+    SEMB_SYM(GroupEnd, "ncclGroupEnd");
+    SEMB_SYM(Send, "ncclSend");
+    SEMB_SYM(Recv, "ncclRecv");
+    SEMB_SYM(AllReduce, "ncclAllReduce");
+    SEMB_SYM(GetErrorString, "ncclGetErrorString");
+#undef SEMB_SYM
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv &&
+           a.AllReduce && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
 
 static inline int vec_grid(int64_t n) {
   int64_t g = (n + VEC_NT - 1) / VEC_NT;
@@ -27,7 +55,7 @@ struct ProfScope {
   int kind;
   cudaEvent_t stop = nullptr;
   ProfScope(semb_ctx* ctx, int k) : c(ctx), kind(k) {
-    if (!c->prof.on) return;
+    if (!c->prof.on || !(c->prof.mask & (1 << k))) return;
     Profile& p = c->prof;
     if (p.used[kind] == p.start[kind].size()) {
       cudaEvent_t a, b;
@@ -155,13 +183,13 @@ static int halo_gather(semb_ctx* c, const double* x, cudaStream_t st, const int*
 }
 static int halo_exchange(semb_ctx* c, cudaStream_t st) {
   if (c->nb_rank.empty()) return 0;
-  SEMB_NCCL(ncclGroupStart());
+  SEMB_NCCL(GroupStart());
   for (size_t q = 0; q < c->nb_rank.size(); ++q) {
     const int64_t off = c->nb_off[q], cnt = c->nb_off[q + 1] - off;
-    SEMB_NCCL(ncclSend(c->hbuf + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
-    SEMB_NCCL(ncclRecv(c->hbuf + c->n_send + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
+    SEMB_NCCL(Send(c->hbuf + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
+    SEMB_NCCL(Recv(c->hbuf + c->n_send + off, (size_t)cnt, ncclDouble, c->nb_rank[q], c->comm, st));
   }
-  SEMB_NCCL(ncclGroupEnd());
+  SEMB_NCCL(GroupEnd());
   return 0;
 }
 static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done) {
@@ -184,7 +212,7 @@ static int gs_full(semb_ctx* c, double* x, const int* done) {
 }
 static int allreduce_sum(semb_ctx* c, double* dev, int count) {
   if (c->comm == nullptr || c->nranks == 1) return 0;
-  SEMB_NCCL(ncclAllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
+  SEMB_NCCL(AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
 
@@ -333,7 +361,7 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->copy_start);
   cudaFree(c->copy_ids);
   cudaFree(c->hbuf);
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_if_done) cudaEventDestroy(c->ev_if_done);
   if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
@@ -883,7 +911,7 @@ int semb_comm_unique_id(char* id128) {
   SEMB_CHECK(id128 != nullptr, "semb_comm_unique_id: NULL argument");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
   ncclUniqueId id;
-  SEMB_NCCL(ncclGetUniqueId(&id));
+  SEMB_NCCL(GetUniqueId(&id));
   std::memcpy(id128, &id, sizeof(id));
   return 0;
 }
@@ -894,7 +922,7 @@ int semb_comm_init(semb_ctx* c, int nranks, int rank, const char* id128) {
   SEMB_TRY(bind_device(c));
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof(id));
-  SEMB_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+  SEMB_NCCL(CommInitRank(&c->comm, nranks, id, rank));
   c->nranks = nranks;
   c->rank = rank;
   SEMB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
@@ -976,6 +1004,7 @@ int semb_profile_enable(semb_ctx* c, int on) {
   SEMB_TRY(bind_device(c));
   if (!on && c->prof.on) SEMB_TRY(prof_flush(c));
   c->prof.on = on != 0;
+  c->prof.mask = on > 1 ? (on >> 1) : 0xffff;  // on = 1: all kernels; on = 1 | (mask << 1): only those in mask
   return 0;
 }
 int semb_profile_reset(semb_ctx* c) {
