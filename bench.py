@@ -34,9 +34,20 @@ N_ORDER = 7
 F_SHARED = 1.0 - ((N_ORDER - 1) / (N_ORDER + 1)) ** 3
 BYTES_AX = 64.0                      # u 8 + six G 48 + w 8 per local node
 BYTES_GS = 20.0 * F_SHARED           # shared nodes: read 8 + index 4 + write 8
-BYTES_UPDATE_PCG = 56.0 + 8.0        # x,p,r,Ap,rmult reads + x,r writes (+ dinv)
+BYTES_UPDATE_PCG = 49.0 + 8.0        # x,p,r,Ap reads 32 + 1-byte multiplicity + x,r writes 16 (+ dinv 8)
 BYTES_DIR_PCG = 24.0 + 8.0           # r,p reads + p write (+ dinv)
 TOL = 1e-8
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the fused Ax kernel from the committed ncu capture
+    (profiles/ax_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    path = os.path.join(ROOT, "profiles", "ax_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -48,9 +59,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons; samples are kept with their
+    timestamps and only those inside the timed window are summarised."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -64,12 +76,15 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
+        """Summarise the samples taken between the two time.time() stamps."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -78,7 +93,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, mx, pw = [], set(), None, []
+        sm, reasons, mx, pw, all_sm = [], set(), None, [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
@@ -86,23 +101,30 @@ class ClockSampler:
                 if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx = float(f[2])
-                    pw.append(float(f[3]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    clk, mxv, pwv = float(f[1]), float(f[2]), float(f[3])
                 except ValueError:
                     continue
-                for nm, val in zip(names, f[4:8]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
+                mx = mxv
+                all_sm.append(clk)
+                if t_begin - 0.02 <= ts <= t_end + 0.02:
+                    sm.append(clk)
+                    pw.append(pwv)
+                    for nm, val in zip(names, f[4:8]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
             os.unlink(self.path)
         except Exception:
             pass
         if sm:
-            top = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half when idle ones leak in
-            out["sm_mhz"] = float(np.median(top))
-            out["sm_max_mhz"] = mx
-            out["power_w_max"] = max(pw) if pw else None
+            out["sm_mhz"] = float(np.median(sm))
+            out["power_w_max"] = max(pw)
             out["samples"] = len(sm)
+        elif all_sm:
+            out["sm_mhz"] = float(np.median(all_sm))
+            out["samples"] = 0
+            out["note"] = "no sample fell inside the timed window; median over the whole run"
+        out["sm_max_mhz"] = mx
         out["reasons"] = sorted(reasons)
         return out
 
@@ -240,6 +262,8 @@ def run_ours(args):
         return elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
 
     # ---- device-resident arm -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         x_dev, niter = solve_dev()
     sync_all()
@@ -248,10 +272,9 @@ def run_ours(args):
     _capi.check(lib.semb_profile_enable(ctx.handle, 1 | ((1 << _capi.K_AX) << 1)))
     _capi.check(lib.semb_profile_reset(ctx.handle))
     launches0 = lib.semb_launch_count(ctx.handle)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    wall0 = time.time()
     ev0.record()
     iters_total = 0
     for _ in range(args.steps):
@@ -259,7 +282,7 @@ def run_ours(args):
         iters_total += niter
     ev1.record()
     sync_all()
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, time.time())
     ms_total = over_ranks(ev0.elapsed_time(ev1), "MAX")
     dof_all = over_ranks(dof, "SUM")
     launches = lib.semb_launch_count(ctx.handle) - launches0
@@ -278,21 +301,22 @@ def run_ours(args):
     _capi.check(lib.semb_profile_enable(ctx.handle, 1))
     _capi.check(lib.semb_profile_reset(ctx.handle))
     ev0.record()
-    solve_dev()
+    _, iters_pass2 = solve_dev()
     ev1.record()
     sync_all()
     ms_pass2 = ev0.elapsed_time(ev1)
     kern2 = read_profile([("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE), ("direction", _capi.K_DIRECTION)])
     _capi.check(lib.semb_profile_enable(ctx.handle, 0))
     value = dof_all * iters_total / (ms_total * 1e-3) / 1e9
-    ax_ms = kern["ax"][0] / max(kern["ax"][1], 1)
+    # per CG iteration: with a halo the Ax of one iteration is two launches (interface elements, then the rest)
+    ax_ms = kern["ax"][0] / max(iters_total, 1)
     ax_gbs = BYTES_AX * dof / (ax_ms * 1e-3) / 1e9
 
     def kernel_entry(name, bytes_per_dof):
         tot, cnt = kern2[name]
-        ms = tot / max(cnt, 1)
+        ms = tot / max(iters_pass2, 1)
         gbs = bytes_per_dof * dof / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"ms": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs, "frac": gbs / peak,
+        return {"ms_per_iteration": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs, "frac": gbs / peak,
                 "share_of_step": tot / ms_pass2}
 
     # ---- fused Ax + mask + gather-scatter alone (the north-star 70 % target) ----
@@ -371,8 +395,10 @@ def run_ours(args):
         "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + BYTES_GS, "achieved_gbs": axgs_gbs,
                   "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
         "roofline": {"bound": "hbm", "kernel": "ax8_kernel (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
-                     "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak, "traffic": None,
-                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "launches_timed": kern["ax"][1],
+                     "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak,
+                     "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if world == 1 and nel == 32 else None,
+                     "traffic_source": (ncu_traffic() or {}).get("source"), "algorithmic_bytes_per_launch": BYTES_AX * dof,
+                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "avg_ms_is": "per CG iteration", "launches_timed": kern["ax"][1],
                      "share_of_step": kern["ax"][0] / ms_total, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
         "kernels": {"ax": kernel_entry("ax", BYTES_AX), "gs": kernel_entry("gs", BYTES_GS),
                     "update": kernel_entry("update", BYTES_UPDATE_PCG), "direction": kernel_entry("direction", BYTES_DIR_PCG)},
@@ -391,7 +417,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2)")

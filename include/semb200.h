@@ -165,6 +165,10 @@ int semb_profile_reset(semb_ctx* ctx);
 int semb_profile_get(semb_ctx* ctx, int kernel, double* total_ms, int64_t* launches);
 /* Kernels launched by this context since creation (all kinds). */
 int64_t semb_launch_count(semb_ctx* ctx);
+/* Process-wide tuning knobs for A/B measurements; results do not depend on
+ * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
+ * factors in the N = 7 Ax kernel. */
+int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ SIGNATURES = {
     "semb_profile_reset": (C.c_int, [C.c_void_p]),
     "semb_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "semb_launch_count": (C.c_int64, [C.c_void_p]),
+    "semb_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 

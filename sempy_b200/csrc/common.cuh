@@ -143,6 +143,7 @@ struct semb_ctx {
   int64_t gs_var_off = 0;
   bool have_gs = false;
   double* rmult = nullptr;
+  unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 
   // Dirichlet mask: 1 bit per local node (1 = zeroed) + the id list
   uint32_t* maskbits = nullptr;

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <utility>
@@ -14,6 +15,13 @@ namespace semb {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+// tuning knob for A/B measurements: bulk L2 prefetch of G in the Nq = 8 Ax kernel (default on);
+// SEMB_AX_L2_PREFETCH=0 or semb_set_tuning("ax_l2_prefetch", 0) turns it off
+static int g_ax_l2_prefetch = [] {
+  const char* v = getenv("SEMB_AX_L2_PREFETCH");
+  return v ? atoi(v) : 1;
+}();
 
 const NcclApi& nccl() {
   static NcclApi api = [] {
@@ -127,7 +135,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
       attr_done[c->device & 63] = true;
     }
 #define SEMB_LAUNCH_8(M, DT) \
-  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, d8, done)
+  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, d8, done, g_ax_l2_prefetch)
     if (mask && dot) SEMB_LAUNCH_8(true, true);
     else if (mask) SEMB_LAUNCH_8(true, false);
     else if (dot) SEMB_LAUNCH_8(false, true);
@@ -218,7 +226,7 @@ static int allreduce_sum(semb_ctx* c, double* dev, int count) {
 
 static int reduce_partials(semb_ctx* c, int64_t n, int64_t stride, int nout, double* out, const int* done) {
   c->launch_count++;
-  reduce_partials_kernel<<<1, VEC_NT, 0, c->stream>>>(c->partials, n, stride, nout, out, done);
+  reduce_partials_kernel<<<1, RED_NT, 0, c->stream>>>(c->partials, n, stride, nout, out, done);
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -261,9 +269,10 @@ static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
 // rmult = 1 / gs(ones)   (sempy/mesh.py:440-442); across ranks when a halo is set
 static int build_rmult(semb_ctx* c) {
   if (!c->rmult) SEMB_CUDA(cudaMalloc(&c->rmult, sizeof(double) * (size_t)c->n));
+  if (!c->mult) SEMB_CUDA(cudaMalloc(&c->mult, (size_t)c->n + 16));
   fill_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, 1.0, c->n);
   SEMB_TRY(gs_full(c, c->rmult, nullptr));
-  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->n);
+  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->mult, c->n);
   SEMB_CUDA(cudaGetLastError());
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->vec[4]) {  // cached Jacobi diagonal is stale
@@ -343,6 +352,7 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->gs_ids);
   cudaFree(c->gs_var_start);
   cudaFree(c->rmult);
+  cudaFree(c->mult);
   cudaFree(c->maskbits);
   cudaFree(c->mask_ids);
   cudaFree(c->partials);
@@ -453,8 +463,11 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
     const int k = len == 2 ? 0 : len == 4 ? 1 : len == 8 ? 2 : 3;
     cls[k].emplace_back((int32_t)first, s);
   }
-  // Order segments by their first local index: neighbouring threads then touch neighbouring memory.
-  for (auto& v : cls) std::sort(v.begin(), v.end());
+  // Order segments by their first local index so that neighbouring threads touch neighbouring
+  // memory -- DESCENDING: the operator kernel before the gather-scatter writes its output in ascending
+  // element order, so its tail is what is still in L2; walking backwards reads that first, and leaves
+  // the head of the vector in L2 for the ascending update kernel that follows.
+  for (auto& v : cls) std::sort(v.begin(), v.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& b) { return a > b; });
   std::vector<int32_t> ids;
   std::vector<int32_t> var_start;
   c->gs_classes.clear();
@@ -791,14 +804,19 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
       {
         ProfScope ps(c, SEMB_K_UPDATE);
         c->launch_count++;
-        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->rmult, dinv, s, n, c->partials);
-        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->rmult, nullptr, s, n, c->partials);
+        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, s, n, c->partials);
+        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, nullptr, s, n, c->partials);
         SEMB_CUDA(cudaGetLastError());
       }
-      SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
-      SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
-      c->launch_count++;
-      cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
+      if (c->comm != nullptr && c->nranks > 1) {
+        SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
+        SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
+        c->launch_count++;
+        cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
+      } else {
+        c->launch_count++;
+        reduce_and_step_kernel<<<1, RED_NT, 0, c->stream>>>(c->partials, grid, s, hist);
+      }
       SEMB_CUDA(cudaGetLastError());
       // p = z + beta p                          (elliptic.py:70)
       {
@@ -851,7 +869,7 @@ int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_a
   }
   auto dot = [&](const double* a, const double* bb, double* out_dev, double* out_host) -> int {
     dot_kernel<false><<<grid, VEC_NT>>>(a, bb, nullptr, n, partials);
-    reduce_partials_kernel<<<1, VEC_NT>>>(partials, grid, 0, 1, out_dev, nullptr);
+    reduce_partials_kernel<<<1, RED_NT>>>(partials, grid, 0, 1, out_dev, nullptr);
     SEMB_CUDA(cudaGetLastError());
     SEMB_CUDA(cudaMemcpy(out_host, out_dev, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
@@ -1026,5 +1044,15 @@ int semb_profile_get(semb_ctx* c, int kernel, double* total_ms, int64_t* launche
   return 0;
 }
 int64_t semb_launch_count(semb_ctx* c) { return c ? c->launch_count : -1; }
+
+int semb_set_tuning(const char* name, int value) {
+  SEMB_CHECK(name != nullptr, "semb_set_tuning: NULL name");
+  if (std::strcmp(name, "ax_l2_prefetch") == 0) {
+    g_ax_l2_prefetch = value;
+    return 0;
+  }
+  set_error(std::string("semb_set_tuning: unknown knob ") + name);
+  return 2;
+}
 
 }  // extern "C"

@@ -140,16 +140,35 @@ __device__ __forceinline__ double block_sum(double v) {
   return s_out;
 }
 
-// out[q] = sum(partials[q*stride .. q*stride + n)) for q < nout (one CTA).
-__global__ void __launch_bounds__(VEC_NT)
+// out[q] = sum(partials[q*stride .. q*stride + n)) for q < nout (one CTA of 1024 threads, fixed order).
+constexpr int RED_NT = 1024;
+__global__ void __launch_bounds__(RED_NT)
 reduce_partials_kernel(const double* __restrict__ partials, int64_t n, int64_t stride, int nout,
                        double* __restrict__ out, const int* __restrict__ done) {
   if (done != nullptr && *done) return;
+  __shared__ double s_red[RED_NT / 32];
   for (int q = 0; q < nout; ++q) {
-    double v = 0.0;
-    for (int64_t t = threadIdx.x; t < n; t += VEC_NT) v += partials[q * stride + t];
-    const double s = block_sum(v);
-    if (threadIdx.x == 0) out[q] = s;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    const double* src = partials + q * stride;
+    int64_t t = threadIdx.x;
+    for (; t + 3 * RED_NT < n; t += 4 * RED_NT) {
+      v0 += src[t];
+      v1 += src[t + RED_NT];
+      v2 += src[t + 2 * RED_NT];
+      v3 += src[t + 3 * RED_NT];
+    }
+    for (; t < n; t += RED_NT) v0 += src[t];
+    double v = (v0 + v1) + (v2 + v3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double w = s_red[threadIdx.x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+      if (threadIdx.x == 0) out[q] = w;
+    }
     __syncthreads();
   }
 }
@@ -220,10 +239,12 @@ __global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double t
 // K3: x += alpha p ; r -= alpha Ap ; partial of sum rmult r r (or rmult r dinv r)
 // (sempy/elliptic.py:52-60; iterative.py:66-73).  56 B per node (+8 Jacobi).
 // ---------------------------------------------------------------------------
+// The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node);
+// __drcp_rn(count) is the correctly rounded 1.0/count, i.e. exactly the stored rmult.
 template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                 const double* __restrict__ Ap, const double* __restrict__ rmult, const double* __restrict__ dinv,
+                 const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
                  const CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials) {
   if (s->done) return;
   const double alpha = s->rdotr / s->pAp;
@@ -233,10 +254,11 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   double2* r2 = reinterpret_cast<double2*>(r);
   const double2* p2 = reinterpret_cast<const double2*>(p);
   const double2* a2 = reinterpret_cast<const double2*>(Ap);
-  const double2* m2 = reinterpret_cast<const double2*>(rmult);
+  const uchar2* m2 = reinterpret_cast<const uchar2*>(mult);
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
   for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    const double2 pv = p2[q], av = a2[q], mv = m2[q];
+    const double2 pv = p2[q], av = a2[q];
+    const uchar2 mc = m2[q];
     double2 xv = x2[q], rv = r2[q];
     xv.x = xv.x + alpha * pv.x;
     xv.y = xv.y + alpha * pv.y;
@@ -244,13 +266,14 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
     rv.y = rv.y - alpha * av.y;
     x2[q] = xv;
     r2[q] = rv;
+    const double wx = __drcp_rn((double)mc.x), wy = __drcp_rn((double)mc.y);
     if (JACOBI) {
       const double2 dv = d2[q];
-      acc = fma(mv.x * rv.x, dv.x * rv.x, acc);
-      acc = fma(mv.y * rv.y, dv.y * rv.y, acc);
+      acc = fma(wx * rv.x, dv.x * rv.x, acc);
+      acc = fma(wy * rv.y, dv.y * rv.y, acc);
     } else {
-      acc = fma(mv.x * rv.x, rv.x, acc);
-      acc = fma(mv.y * rv.y, rv.y, acc);
+      acc = fma(wx * rv.x, rv.x, acc);
+      acc = fma(wy * rv.y, rv.y, acc);
     }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -259,7 +282,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
     const double rv = r[q] - alpha * Ap[q];
     x[q] = xv;
     r[q] = rv;
-    acc = fma(rmult[q] * rv, JACOBI ? dinv[q] * rv : rv, acc);
+    acc = fma(__drcp_rn((double)mult[q]) * rv, JACOBI ? dinv[q] * rv : rv, acc);
   }
   const double sum = block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = sum;
@@ -267,8 +290,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
 
 // After the update's reduction: beta, history, iteration count, stop test
 // (sempy/elliptic.py:47,59-71).
-__global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
-  if (s->done) return;
+__device__ __forceinline__ void cg_step_scalars(CgScalars* s, double* hist) {
   const double r0 = s->rdotr, r1 = s->rdotr_new;
   const double alpha = r0 / s->pAp;
   const double beta = r1 / r0;
@@ -285,6 +307,37 @@ __global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
   s->rdotr = r1;
   s->niter += 1;
   s->done = !(s->niter < s->maxit && r1 > s->TOL) ? 1 : 0;
+}
+__global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
+  if (s->done) return;
+  cg_step_scalars(s, hist);
+}
+// single GPU: reduction of the update's partials and the scalar step in one launch
+__global__ void __launch_bounds__(RED_NT)
+reduce_and_step_kernel(const double* __restrict__ partials, int64_t n, CgScalars* s, double* hist) {
+  if (s->done) return;
+  __shared__ double s_red[RED_NT / 32];
+  double v0 = 0.0, v1 = 0.0;
+  int64_t t = threadIdx.x;
+  for (; t + RED_NT < n; t += 2 * RED_NT) {
+    v0 += partials[t];
+    v1 += partials[t + RED_NT];
+  }
+  for (; t < n; t += RED_NT) v0 += partials[t];
+  double v = v0 + v1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double w = s_red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) {
+      s->rdotr_new = w;
+      cg_step_scalars(s, hist);
+    }
+  }
 }
 
 // K4: p = z + beta p with z = r or dinv r (sempy/elliptic.py:70; iterative.py:83). 24 B per node.
@@ -329,9 +382,12 @@ __global__ void jacobi_invert_kernel(double* __restrict__ d, const uint32_t* __r
 __global__ void fill_kernel(double* __restrict__ x, double v, int64_t n) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) x[q] = v;
 }
-__global__ void reciprocal_kernel(double* __restrict__ x, int64_t n) {
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
-    x[q] = 1.0 / x[q];
+__global__ void reciprocal_kernel(double* __restrict__ x, unsigned char* __restrict__ count, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const double c = x[q];  // exact small integer: sum of ones
+    count[q] = (unsigned char)(c < 255.0 ? c : 255.0);
+    x[q] = 1.0 / c;
+  }
 }
 
 // ---- generic-operator CG pieces (sempy/iterative.py) ----------------------
