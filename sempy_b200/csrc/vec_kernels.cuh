@@ -239,14 +239,19 @@ __global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double t
 // K3: x += alpha p ; r -= alpha Ap ; partial of sum rmult r r (or rmult r dinv r)
 // (sempy/elliptic.py:52-60; iterative.py:66-73).  56 B per node (+8 Jacobi).
 // ---------------------------------------------------------------------------
-// The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node);
-// __drcp_rn(count) is the correctly rounded 1.0/count, i.e. exactly the stored rmult.
+// The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node) and
+// turned back into the identical double through a small shared-memory table of 1.0/c (a division in
+// the loop costs a MUFU + Newton sequence with a slow-path call per element and made the kernel
+// 16 % slower than reading the 8-byte weights).
 template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                  const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
                  const CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials) {
   if (s->done) return;
+  __shared__ double s_rcp[256];
+  s_rcp[threadIdx.x] = 1.0 / (double)(threadIdx.x > 0 ? threadIdx.x : 1);  // VEC_NT == 256 entries
+  __syncthreads();
   const double alpha = s->rdotr / s->pAp;
   double acc = 0.0;
   const int64_t n2 = n >> 1;
@@ -266,7 +271,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
     rv.y = rv.y - alpha * av.y;
     x2[q] = xv;
     r2[q] = rv;
-    const double wx = __drcp_rn((double)mc.x), wy = __drcp_rn((double)mc.y);
+    const double wx = s_rcp[mc.x], wy = s_rcp[mc.y];
     if (JACOBI) {
       const double2 dv = d2[q];
       acc = fma(wx * rv.x, dv.x * rv.x, acc);
@@ -282,7 +287,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
     const double rv = r[q] - alpha * Ap[q];
     x[q] = xv;
     r[q] = rv;
-    acc = fma(__drcp_rn((double)mult[q]) * rv, JACOBI ? dinv[q] * rv : rv, acc);
+    acc = fma(s_rcp[mult[q]] * rv, JACOBI ? dinv[q] * rv : rv, acc);
   }
   const double sum = block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = sum;

@@ -68,13 +68,13 @@ def _worker(rank, size, port, dims, perturb, N, out):
         b = 3 * np.pi ** 2 * np.sin(np.pi * gx) * np.sin(np.pi * gy) * np.sin(np.pi * gz) * mass * jaco
         b = so.gather_scatter(b.reshape(-1), g2l, gs) * mask
         axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
-        xo, ito = so.elliptic_cg(axo, mask, g2l, gs, rmult, b, tol=1e-12, maxit=3000)
-        xg, itg = elliptic_cg(m, take(b), tol=1e-12, maxit=3000)
+        xo, ito = so.elliptic_cg(axo, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
+        xg, itg = elliptic_cg(m, take(b), tol=1e-10, maxit=3000)
         errs["cg_iters"] = float(abs(itg - ito))
         errs["cg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
         dinv = mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
-        xo, ito = so.elliptic_pcg_jacobi(axo, dinv, mask, g2l, gs, rmult, b, tol=1e-12, maxit=3000)
-        xg, itg = elliptic_pcg(m, take(b), tol=1e-12, maxit=3000)
+        xo, ito = so.elliptic_pcg_jacobi(axo, dinv, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
+        xg, itg = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
         errs["pcg_iters"] = float(abs(itg - ito))
         errs["pcg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
         res = comm.allgather(errs)

