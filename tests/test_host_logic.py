@@ -98,3 +98,10 @@ def test_numbering_generated_boxes():
         assert gs.size - 1 == np.prod([d * N + 1 for d in dims])
         gid_o, g2l_o, gs_o = so.global_numbering_literal(xe, ye, ze)
         assert np.array_equal(gid, gid_o) and np.array_equal(g2l, g2l_o) and np.array_equal(gs, gs_o)
+
+
+def test_bundled_meshes_load():
+    for name, ne in (("box001.msh", 1), ("box002.msh", 2), ("box004.msh", 4), ("box008.msh", 8)):
+        m = pm.load_mesh(name)
+        assert m.get_num_elems() == ne and m.get_ndim() == 3
+        assert m.x.min() == 0.0 and m.z.max() == 1.0
