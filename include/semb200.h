@@ -149,6 +149,17 @@ int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* 
                   const int32_t* send_ids, int64_t n_if, const int64_t* src_start, const int32_t* src_off,
                   const int64_t* copy_start, const int32_t* copy_ids, int64_t n_if_elems);
 
+/* Peer-memory transport (NVLink / NVSwitch, one node): after semb_set_halo each rank allocates its
+ * receive region and publishes a 64-byte CUDA IPC handle (semb_p2p_alloc); the caller gathers all
+ * ranks' handles (nranks * 64 bytes, rank order) and, for each of this rank's neighbours q (in the
+ * order given to semb_set_halo), the entry offset at which this rank's block starts in q's receive
+ * layout (= the sum of q's nb_count over q's neighbours listed before this rank), and hands both to
+ * semb_p2p_attach.  From then on the halo exchange is written straight into the neighbour's memory by
+ * the gather kernel and the CG dots are summed by a one-CTA peer-memory all-reduce; NCCL stays as the
+ * fallback (semb_set_tuning("p2p", 0)). */
+int semb_p2p_alloc(semb_ctx* ctx, char* handle64);
+int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv_off);
+
 /* ---- device memory helpers for callers without their own allocator ------ */
 int semb_malloc(int device, void** ptr, int64_t bytes);
 int semb_free(int device, void* ptr);
@@ -167,7 +178,8 @@ int semb_profile_get(semb_ctx* ctx, int kernel, double* total_ms, int64_t* launc
 int64_t semb_launch_count(semb_ctx* ctx);
 /* Process-wide tuning knobs for A/B measurements; results do not depend on
  * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
- * factors in the N = 7 Ax kernel. */
+ * factors in the N = 7 Ax kernel.  "p2p": 1 (default) / 0, peer-memory transport
+ * vs NCCL for the halo exchange and the scalar all-reduces. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

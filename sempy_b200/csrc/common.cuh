@@ -109,6 +109,15 @@ struct GsClass {
   int64_t off;
 };
 
+constexpr int LL_MAXR = 16;  // ranks supported by the peer-memory path (one NVSwitch domain)
+constexpr int LL_MAXV = 4;   // doubles per scalar all-reduce
+struct HaloPeers {
+  int nneigh;
+  int rank_of[LL_MAXR];
+  int64_t off[LL_MAXR + 1];   // my send blocks (entries)
+  int64_t peer_off[LL_MAXR];  // start of my block in that neighbour's halo part (entries)
+};
+
 struct Profile {
   bool on = false;
   int mask = 0xffff;
@@ -179,6 +188,17 @@ struct semb_ctx {
   int32_t* copy_ids = nullptr;
   double* hbuf = nullptr;          // [send region | receive region]
   int64_t n_if_elems = 0;          // elements [0, n_if_elems) touch the interface
+
+  // peer-memory path (NVLink): every rank maps every other rank's "LL" region (cudaIpc) and writes
+  // {32-bit data, 32-bit sequence} words straight into it; the reader spins on the sequence number
+  // (NCCL's LL idea), so neither the scalar all-reduce nor the halo exchange needs a NCCL call.
+  bool p2p = false;
+  unsigned long long* ll_local = nullptr;  // this rank's region
+  std::vector<unsigned long long*> ll_peer;  // every rank's region as mapped here ([rank] = ll_local)
+  unsigned long long** ll_peer_dev = nullptr;
+  int64_t ll_halo_cap = 0;                 // doubles per parity in the halo part
+  semb::HaloPeers halo_peers;              // neighbour ranks, my send blocks, where they land remotely
+  unsigned int seq_scalar = 0, seq_halo = 0;  // host-side sequence numbers (same on all ranks)
 
   semb::Profile prof;
   int64_t launch_count = 0;

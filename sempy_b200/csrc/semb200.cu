@@ -18,6 +18,10 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 
 // tuning knob for A/B measurements: bulk L2 prefetch of G in the Nq = 8 Ax kernel (default on);
 // SEMB_AX_L2_PREFETCH=0 or semb_set_tuning("ax_l2_prefetch", 0) turns it off
+static int g_p2p_on = [] {  // 0: NCCL for the halo exchange and the scalar all-reduces (A/B against the peer-memory path)
+  const char* v = getenv("SEMB_P2P");
+  return v ? atoi(v) : 1;
+}();
 static int g_ax_l2_prefetch = [] {
   const char* v = getenv("SEMB_AX_L2_PREFETCH");
   return v ? atoi(v) : 1;
@@ -182,15 +186,38 @@ static int launch_gs(semb_ctx* c, double* x, const int* done) {
 }
 
 // ---- multi-GPU halo --------------------------------------------------------
+static inline bool use_p2p(const semb_ctx* c) { return c->p2p && g_p2p_on; }
+
+static HaloPeers make_halo_peers(const semb_ctx* c, const std::vector<int64_t>& peer_off) {
+  HaloPeers hp;
+  std::memset(&hp, 0, sizeof(hp));
+  hp.nneigh = (int)c->nb_rank.size();
+  for (int q = 0; q < hp.nneigh; ++q) {
+    hp.rank_of[q] = c->nb_rank[q];
+    hp.off[q] = c->nb_off[q];
+    hp.peer_off[q] = peer_off[q];
+  }
+  hp.off[hp.nneigh] = c->n_send;
+  return hp;
+}
+
+// gather this rank's partial sums; with the peer-memory path this also delivers them (seq = the
+// exchange's sequence number, advanced by the caller once per exchange)
 static int halo_gather(semb_ctx* c, const double* x, cudaStream_t st, const int* done) {
   if (c->n_send == 0) return 0;
   c->launch_count++;
-  halo_gather_kernel<<<vec_grid(c->n_send), VEC_NT, 0, st>>>(x, c->send_start, c->send_ids, c->n_send, c->hbuf, done);
+  if (use_p2p(c)) {
+    halo_gather_p2p_kernel<<<vec_grid(c->n_send), VEC_NT, 0, st>>>(x, c->send_start, c->send_ids, c->n_send, c->hbuf,
+                                                                   c->ll_peer_dev, c->halo_peers, c->ll_halo_cap,
+                                                                   c->seq_halo, done);
+  } else {
+    halo_gather_kernel<<<vec_grid(c->n_send), VEC_NT, 0, st>>>(x, c->send_start, c->send_ids, c->n_send, c->hbuf, done);
+  }
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
 static int halo_exchange(semb_ctx* c, cudaStream_t st) {
-  if (c->nb_rank.empty()) return 0;
+  if (c->nb_rank.empty() || use_p2p(c)) return 0;
   SEMB_NCCL(GroupStart());
   for (size_t q = 0; q < c->nb_rank.size(); ++q) {
     const int64_t off = c->nb_off[q], cnt = c->nb_off[q + 1] - off;
@@ -203,14 +230,21 @@ static int halo_exchange(semb_ctx* c, cudaStream_t st) {
 static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done) {
   if (c->n_if == 0) return 0;
   c->launch_count++;
-  halo_scatter_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->src_start, c->src_off, c->copy_start,
-                                                           c->copy_ids, c->n_if, done);
+  if (use_p2p(c)) {
+    halo_scatter_p2p_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->ll_local + LL_SCALAR_WORDS, c->n_send,
+                                                                  c->src_start, c->src_off, c->copy_start, c->copy_ids,
+                                                                  c->n_if, c->ll_halo_cap, c->seq_halo, done);
+  } else {
+    halo_scatter_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->src_start, c->src_off, c->copy_start,
+                                                             c->copy_ids, c->n_if, done);
+  }
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
 // Complete gather-scatter of one vector on the context's stream (no overlap).
 static int gs_full(semb_ctx* c, double* x, const int* done) {
   if (c->have_halo) {
+    c->seq_halo++;
     SEMB_TRY(halo_gather(c, x, c->stream, done));
     SEMB_TRY(halo_exchange(c, c->stream));
   }
@@ -220,6 +254,14 @@ static int gs_full(semb_ctx* c, double* x, const int* done) {
 }
 static int allreduce_sum(semb_ctx* c, double* dev, int count) {
   if (c->comm == nullptr || c->nranks == 1) return 0;
+  if (use_p2p(c) && count <= LL_MAXV) {
+    c->seq_scalar++;
+    c->launch_count++;
+    ll_allreduce_kernel<<<1, LL_MAXR * LL_MAXV, 0, c->stream>>>(dev, count, c->ll_peer_dev, c->rank, c->nranks,
+                                                               c->seq_scalar);
+    SEMB_CUDA(cudaGetLastError());
+    return 0;
+  }
   SEMB_NCCL(AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
@@ -371,6 +413,10 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->copy_start);
   cudaFree(c->copy_ids);
   cudaFree(c->hbuf);
+  for (int r = 0; r < (int)c->ll_peer.size(); ++r)
+    if (r != c->rank && c->ll_peer[r]) cudaIpcCloseMemHandle(c->ll_peer[r]);
+  cudaFree(c->ll_local);
+  cudaFree(c->ll_peer_dev);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_if_done) cudaEventDestroy(c->ev_if_done);
@@ -784,6 +830,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, nif, done, 0));
         SEMB_CUDA(cudaEventRecord(c->ev_if_done, c->stream));
         SEMB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_if_done, 0));
+        c->seq_halo++;
         SEMB_TRY(halo_gather(c, Ap, c->comm_stream, done));
         SEMB_CUDA(cudaEventRecord(c->ev_gathered, c->comm_stream));
         SEMB_TRY(halo_exchange(c, c->comm_stream));
@@ -981,7 +1028,52 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
     SEMB_CUDA(cudaMalloc(&c->hbuf, sizeof(double) * 2 * (size_t)c->n_send));
   }
   c->have_halo = c->nranks > 1;
+  if (c->n_send > c->ll_halo_cap) c->p2p = false;  // receive region too small for the new tables: back to NCCL until re-attached
   return build_rmult(c);  // multiplicities now count the copies on the other ranks too
+}
+
+int semb_p2p_alloc(semb_ctx* c, char* handle64) {
+  SEMB_CHECK(c && handle64, "semb_p2p_alloc: NULL argument");
+  SEMB_CHECK(c->comm != nullptr && c->have_halo, "semb_p2p_alloc: call semb_comm_init and semb_set_halo first");
+  SEMB_CHECK(c->nranks <= LL_MAXR, "semb_p2p_alloc: more ranks than the peer-memory path supports");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  SEMB_TRY(bind_device(c));
+  c->ll_halo_cap = std::max<int64_t>(c->n_send, 1);
+  const size_t words = (size_t)LL_SCALAR_WORDS + 2 * 2 * (size_t)c->ll_halo_cap;
+  if (c->ll_local == nullptr) {
+    SEMB_CUDA(cudaMalloc(&c->ll_local, words * sizeof(unsigned long long)));
+    SEMB_CUDA(cudaMemset(c->ll_local, 0, words * sizeof(unsigned long long)));
+    SEMB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  SEMB_CUDA(cudaIpcGetMemHandle(&h, c->ll_local));
+  std::memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+
+int semb_p2p_attach(semb_ctx* c, const char* handles, const int64_t* peer_recv_off) {
+  SEMB_CHECK(c && handles && (peer_recv_off || c->nb_rank.empty()), "semb_p2p_attach: NULL argument");
+  SEMB_CHECK(c->ll_local != nullptr, "semb_p2p_attach: call semb_p2p_alloc first");
+  SEMB_TRY(bind_device(c));
+  c->ll_peer.assign(c->nranks, nullptr);
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) {
+      c->ll_peer[r] = c->ll_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * (size_t)r, sizeof(h));
+    void* ptr = nullptr;
+    SEMB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ll_peer[r] = static_cast<unsigned long long*>(ptr);
+  }
+  SEMB_TRY(upload(&c->ll_peer_dev, c->ll_peer.data(), c->ll_peer.size()));
+  std::vector<int64_t> po(peer_recv_off, peer_recv_off + c->nb_rank.size());
+  c->halo_peers = make_halo_peers(c, po);
+  c->seq_scalar = 0;
+  c->seq_halo = 0;
+  c->p2p = true;
+  return 0;
 }
 
 // ---- memory helpers --------------------------------------------------------
@@ -1049,6 +1141,10 @@ int semb_set_tuning(const char* name, int value) {
   SEMB_CHECK(name != nullptr, "semb_set_tuning: NULL name");
   if (std::strcmp(name, "ax_l2_prefetch") == 0) {
     g_ax_l2_prefetch = value;
+    return 0;
+  }
+  if (std::strcmp(name, "p2p") == 0) {
+    g_p2p_on = value;
     return 0;
   }
   set_error(std::string("semb_set_tuning: unknown knob ") + name);

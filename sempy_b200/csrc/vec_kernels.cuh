@@ -113,6 +113,93 @@ halo_scatter_kernel(double* __restrict__ x, const double* __restrict__ hbuf, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// Peer-memory ("LL") transport over NVLink.  A double travels as two 8-byte words {32 data bits,
+// 32-bit sequence number}; 8-byte stores are atomic, so a reader that sees the expected sequence
+// number in both words has the value -- no fences, no separate flag, no NCCL call.
+// Region layout per rank (in 8-byte words): scalars [2 parity][LL_MAXR ranks][LL_MAXV values][2],
+// then the halo part [2 parity][ll_halo_cap doubles][2].
+// ---------------------------------------------------------------------------
+constexpr int64_t LL_SCALAR_WORDS = 2 * LL_MAXR * LL_MAXV * 2;
+
+__device__ __forceinline__ void ll_store(unsigned long long* dst, double v, unsigned int seq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(lo), "r"(seq) : "memory");
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 1), "r"(hi), "r"(seq) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* src, unsigned int seq) {
+  unsigned int lo, hi, f0, f1;
+  do {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(f0) : "l"(src) : "memory");
+  } while (f0 != seq);
+  do {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(f1) : "l"(src + 1) : "memory");
+  } while (f1 != seq);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+
+// In-place sum of `count` doubles over all ranks; every rank adds in ascending rank order, so the
+// result is bitwise identical everywhere.  One CTA of LL_MAXR*LL_MAXV threads.
+__global__ void __launch_bounds__(LL_MAXR* LL_MAXV)
+ll_allreduce_kernel(double* vals, int count, unsigned long long* const* __restrict__ peers, int rank, int nranks,
+                    unsigned int seq) {
+  __shared__ double s_v[LL_MAXR][LL_MAXV];
+  const int r = threadIdx.x / LL_MAXV, cidx = threadIdx.x % LL_MAXV;
+  const int64_t slot = (int64_t)(seq & 1) * (LL_MAXR * LL_MAXV * 2);
+  if (r < nranks && cidx < count) {
+    // my value cidx -> rank r's region, slot [parity][my rank][cidx]
+    ll_store(peers[r] + slot + ((int64_t)rank * LL_MAXV + cidx) * 2, vals[cidx], seq);
+  }
+  if (r < nranks && cidx < count) {
+    s_v[r][cidx] = ll_load(peers[rank] + slot + ((int64_t)r * LL_MAXV + cidx) * 2, seq);
+  }
+  __syncthreads();
+  if (threadIdx.x < count) {
+    double sum = 0.0;
+    for (int q = 0; q < nranks; ++q) sum += s_v[q][threadIdx.x];
+    vals[threadIdx.x] = sum;
+  }
+}
+
+// halo_gather + remote write: the partial sum of send entry t goes to hbuf[t] (own use) and, as LL
+// words, straight into the neighbour's halo part over NVLink.
+__global__ void __launch_bounds__(VEC_NT)
+halo_gather_p2p_kernel(const double* __restrict__ x, const int64_t* __restrict__ start, const int32_t* __restrict__ ids,
+                       int64_t nent, double* __restrict__ hbuf, unsigned long long* const* __restrict__ peers,
+                       const HaloPeers hp, int64_t halo_cap, unsigned int seq, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  const int64_t par = (int64_t)(seq & 1) * halo_cap * 2;
+  for (int64_t t = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; t < nent; t += (int64_t)gridDim.x * VEC_NT) {
+    double s = 0.0;
+    for (int64_t q = start[t]; q < start[t + 1]; ++q) s += x[ids[q]];
+    hbuf[t] = s;
+    int nb = 0;
+    while (nb + 1 < hp.nneigh && t >= hp.off[nb + 1]) ++nb;
+    unsigned long long* dst = peers[hp.rank_of[nb]] + LL_SCALAR_WORDS + par + (hp.peer_off[nb] + (t - hp.off[nb])) * 2;
+    ll_store(dst, s, seq);
+  }
+}
+
+// halo_scatter reading the neighbours' partial sums from this rank's own LL region (spins until they
+// have arrived); same ascending-rank summation order as the NCCL form.
+__global__ void __launch_bounds__(VEC_NT)
+halo_scatter_p2p_kernel(double* __restrict__ x, const double* __restrict__ hbuf, const unsigned long long* __restrict__ ll_halo,
+                        int64_t n_send, const int64_t* __restrict__ src_start, const int32_t* __restrict__ src_off,
+                        const int64_t* __restrict__ copy_start, const int32_t* __restrict__ copy_ids, int64_t n_if,
+                        int64_t halo_cap, unsigned int seq, const int* __restrict__ done) {
+  if (done != nullptr && *done) return;
+  const unsigned long long* base = ll_halo + (int64_t)(seq & 1) * halo_cap * 2;
+  for (int64_t i = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; i < n_if; i += (int64_t)gridDim.x * VEC_NT) {
+    double s = 0.0;
+    for (int64_t q = src_start[i]; q < src_start[i + 1]; ++q) {
+      const int64_t off = src_off[q];
+      s += off < n_send ? hbuf[off] : ll_load(base + (off - n_send) * 2, seq);
+    }
+    for (int64_t q = copy_start[i]; q < copy_start[i + 1]; ++q) x[copy_ids[q]] = s;
+  }
+}
+
 // x[mask_ids] = 0   (Mesh.apply_mask, sempy/mesh.py:487-494, as an index list)
 __global__ void mask_kernel(double* __restrict__ x, const int64_t* __restrict__ ids, int64_t n) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)

@@ -387,6 +387,22 @@ class Mesh:
         _capi.check(lib.semb_set_halo(ctx.handle, keep[0].size, keep[0].ctypes.data, keep[1].ctypes.data,
                                       keep[2].ctypes.data, keep[3].ctypes.data, h["n_if"], keep[4].ctypes.data,
                                       keep[5].ctypes.data, keep[6].ctypes.data, keep[7].ctypes.data, self._n_if_elems))
+        if os.environ.get("SEMB_P2P", "1") != "0" and not getattr(ctx, "p2p_ready", False):
+            # peer-memory transport: publish this rank's receive region, map everybody else's
+            handle = C.create_string_buffer(64)
+            _capi.check(lib.semb_p2p_alloc(ctx.handle, handle))
+            everyone = self.comm.allgather((bytes(handle.raw), [int(q) for q in h["nb_rank"]],
+                                            [int(n) for n in h["nb_count"]]))
+            me = self.comm.rank
+            peer_off = []
+            for q in h["nb_rank"]:
+                _hq, ranks_q, counts_q = everyone[int(q)]
+                at = ranks_q.index(me)
+                peer_off.append(sum(counts_q[:at]))
+            peer_off = np.ascontiguousarray(peer_off, dtype=np.int64)
+            blob = b"".join(e[0] for e in everyone)
+            _capi.check(lib.semb_p2p_attach(ctx.handle, blob, peer_off.ctypes.data))
+            ctx.p2p_ready = True
 
     def _vector_args(self, x, name):
         """(pointer, mem flag, keep-alive) for an in-place vector argument."""
