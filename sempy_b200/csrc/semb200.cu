@@ -823,8 +823,23 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
     for (int it = 0; it < todo; ++it) {
       // Ap = mask(A p), local pAp partials      (elliptic.py:48-51)
       // Ap = dssum(Ap)                          (elliptic.py:54)
-      if (c->have_halo) {
-        // slab interface first; its partial sums travel to the neighbours while the interior runs
+      if (c->have_halo && use_p2p(c)) {
+        // Peer-memory path: one Ax launch; the gather kernel writes this rank's interface sums straight
+        // into the neighbours' memory, the local gather-scatter (80 us) hides the NVLink flight time, the
+        // scatter kernel picks the neighbours' sums up from local memory.  One stream, no NCCL call.
+        const int64_t np = ax_num_partials(c, 0, c->E);
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done, 0));
+        c->seq_scalar++;
+        c->launch_count++;
+        reduce_allreduce_kernel<false><<<1, RED_NT, 0, c->stream>>>(c->partials, np, &s->pAp, s, hist, c->ll_peer_dev,
+                                                                    c->rank, c->nranks, c->seq_scalar);
+        SEMB_CUDA(cudaGetLastError());
+        c->seq_halo++;
+        SEMB_TRY(halo_gather(c, Ap, c->stream, done));
+        SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
+      } else if (c->have_halo) {
+        // NCCL path: slab interface first; its partial sums travel to the neighbours while the interior runs
         const int64_t nif = c->n_if_elems;
         const int64_t np1 = ax_num_partials(c, 0, nif);
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, nif, done, 0));
@@ -855,7 +870,12 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, nullptr, s, n, c->partials);
         SEMB_CUDA(cudaGetLastError());
       }
-      if (c->comm != nullptr && c->nranks > 1) {
+      if (c->comm != nullptr && c->nranks > 1 && use_p2p(c)) {
+        c->seq_scalar++;
+        c->launch_count++;
+        reduce_allreduce_kernel<true><<<1, RED_NT, 0, c->stream>>>(c->partials, grid, &s->rdotr_new, s, hist,
+                                                                   c->ll_peer_dev, c->rank, c->nranks, c->seq_scalar);
+      } else if (c->comm != nullptr && c->nranks > 1) {
         SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
         SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
         c->launch_count++;

@@ -140,18 +140,17 @@ __device__ __forceinline__ double ll_load(const unsigned long long* src, unsigne
 }
 
 // In-place sum of `count` doubles over all ranks; every rank adds in ascending rank order, so the
-// result is bitwise identical everywhere.  One CTA of LL_MAXR*LL_MAXV threads.
-__global__ void __launch_bounds__(LL_MAXR* LL_MAXV)
-ll_allreduce_kernel(double* vals, int count, unsigned long long* const* __restrict__ peers, int rank, int nranks,
-                    unsigned int seq) {
+// result is bitwise identical everywhere.  Runs on the first LL_MAXR*LL_MAXV threads of one CTA
+// (all threads of the CTA must call it).
+__device__ __forceinline__ void ll_allreduce_cta(double* vals, int count, unsigned long long* const* __restrict__ peers,
+                                                 int rank, int nranks, unsigned int seq) {
   __shared__ double s_v[LL_MAXR][LL_MAXV];
   const int r = threadIdx.x / LL_MAXV, cidx = threadIdx.x % LL_MAXV;
   const int64_t slot = (int64_t)(seq & 1) * (LL_MAXR * LL_MAXV * 2);
-  if (r < nranks && cidx < count) {
+  const bool mine = threadIdx.x < LL_MAXR * LL_MAXV && r < nranks && cidx < count;
+  if (mine) {
     // my value cidx -> rank r's region, slot [parity][my rank][cidx]
     ll_store(peers[r] + slot + ((int64_t)rank * LL_MAXV + cidx) * 2, vals[cidx], seq);
-  }
-  if (r < nranks && cidx < count) {
     s_v[r][cidx] = ll_load(peers[rank] + slot + ((int64_t)r * LL_MAXV + cidx) * 2, seq);
   }
   __syncthreads();
@@ -160,6 +159,12 @@ ll_allreduce_kernel(double* vals, int count, unsigned long long* const* __restri
     for (int q = 0; q < nranks; ++q) sum += s_v[q][threadIdx.x];
     vals[threadIdx.x] = sum;
   }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(LL_MAXR* LL_MAXV)
+ll_allreduce_kernel(double* vals, int count, unsigned long long* const* __restrict__ peers, int rank, int nranks,
+                    unsigned int seq) {
+  ll_allreduce_cta(vals, count, peers, rank, nranks, seq);
 }
 
 // halo_gather + remote write: the partial sum of send entry t goes to hbuf[t] (own use) and, as LL
@@ -430,6 +435,37 @@ reduce_and_step_kernel(const double* __restrict__ partials, int64_t n, CgScalars
       cg_step_scalars(s, hist);
     }
   }
+}
+
+// Several GPUs: per-CTA partials -> rank sum -> all-rank sum (peer memory) in ONE launch, optionally
+// followed by the scalar step.  `done` is not consulted for the all-reduce itself: every rank must
+// take part in every exchange.
+template <bool STEP>
+__global__ void __launch_bounds__(RED_NT)
+reduce_allreduce_kernel(const double* __restrict__ partials, int64_t n, double* out, CgScalars* s, double* hist,
+                        unsigned long long* const* __restrict__ peers, int rank, int nranks, unsigned int seq) {
+  __shared__ double s_red[RED_NT / 32];
+  double v0 = 0.0, v1 = 0.0;
+  int64_t t = threadIdx.x;
+  for (; t + RED_NT < n; t += 2 * RED_NT) {
+    v0 += partials[t];
+    v1 += partials[t + RED_NT];
+  }
+  for (; t < n; t += RED_NT) v0 += partials[t];
+  double v = v0 + v1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double w = s_red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) *out = w;
+  }
+  __syncthreads();
+  ll_allreduce_cta(out, 1, peers, rank, nranks, seq);
+  if (STEP && threadIdx.x == 0 && !s->done) cg_step_scalars(s, hist);
 }
 
 // K4: p = z + beta p with z = r or dinv r (sempy/elliptic.py:70; iterative.py:83). 24 B per node.
