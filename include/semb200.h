@@ -151,13 +151,15 @@ int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* 
 
 /* Peer-memory transport (NVLink / NVSwitch, one node): after semb_set_halo each rank allocates its
  * receive region and publishes a 64-byte CUDA IPC handle (semb_p2p_alloc); the caller gathers all
- * ranks' handles (nranks * 64 bytes, rank order) and, for each of this rank's neighbours q (in the
+ * ranks' handles (nranks * 64 bytes, rank order; halo_capacity = the largest interface entry count
+ * of any rank, the same value on every rank) and, for each of this rank's neighbours q (in the
  * order given to semb_set_halo), the entry offset at which this rank's block starts in q's receive
  * layout (= the sum of q's nb_count over q's neighbours listed before this rank), and hands both to
  * semb_p2p_attach.  From then on the halo exchange is written straight into the neighbour's memory by
  * the gather kernel and the CG dots are summed by a one-CTA peer-memory all-reduce; NCCL stays as the
- * fallback (semb_set_tuning("p2p", 0)). */
-int semb_p2p_alloc(semb_ctx* ctx, char* handle64);
+ * fallback (semb_set_tuning("p2p", 0)).  A wait for a peer gives up after 5 s: the call that
+ * synchronises next returns an error instead of hanging the GPU. */
+int semb_p2p_alloc(semb_ctx* ctx, int64_t halo_capacity, char* handle64);
 int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv_off);
 
 /* ---- device memory helpers for callers without their own allocator ------ */

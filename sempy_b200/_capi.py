@@ -66,7 +66,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_int64],
     ),
-    "semb_p2p_alloc": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "semb_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
     "semb_p2p_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
     "semb_free": (C.c_int, [C.c_int, C.c_void_p]),

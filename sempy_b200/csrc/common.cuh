@@ -196,6 +196,7 @@ struct semb_ctx {
   unsigned long long* ll_local = nullptr;  // this rank's region
   std::vector<unsigned long long*> ll_peer;  // every rank's region as mapped here ([rank] = ll_local)
   unsigned long long** ll_peer_dev = nullptr;
+  int* ll_error = nullptr;                 // device flag raised when a peer-memory wait times out
   int64_t ll_halo_cap = 0;                 // doubles per parity in the halo part
   semb::HaloPeers halo_peers;              // neighbour ranks, my send blocks, where they land remotely
   unsigned int seq_scalar = 0, seq_halo = 0;  // host-side sequence numbers (same on all ranks)

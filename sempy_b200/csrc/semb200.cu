@@ -233,7 +233,7 @@ static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done
   if (use_p2p(c)) {
     halo_scatter_p2p_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->ll_local + LL_SCALAR_WORDS, c->n_send,
                                                                   c->src_start, c->src_off, c->copy_start, c->copy_ids,
-                                                                  c->n_if, c->ll_halo_cap, c->seq_halo, done);
+                                                                  c->n_if, c->ll_halo_cap, c->seq_halo, done, c->ll_error);
   } else {
     halo_scatter_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->src_start, c->src_off, c->copy_start,
                                                              c->copy_ids, c->n_if, done);
@@ -258,11 +258,23 @@ static int allreduce_sum(semb_ctx* c, double* dev, int count) {
     c->seq_scalar++;
     c->launch_count++;
     ll_allreduce_kernel<<<1, LL_MAXR * LL_MAXV, 0, c->stream>>>(dev, count, c->ll_peer_dev, c->rank, c->nranks,
-                                                               c->seq_scalar);
+                                                               c->seq_scalar, c->ll_error);
     SEMB_CUDA(cudaGetLastError());
     return 0;
   }
   SEMB_NCCL(AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
+  return 0;
+}
+
+// after a stream synchronisation: did a peer-memory wait time out?
+static int check_ll_error(semb_ctx* c) {
+  if (!c->p2p || c->ll_error == nullptr) return 0;
+  int flag = 0;
+  SEMB_CUDA(cudaMemcpy(&flag, c->ll_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    set_error("peer-memory exchange timed out: a neighbouring rank did not deliver (rank failure or table mismatch)");
+    return 4;
+  }
   return 0;
 }
 
@@ -305,7 +317,7 @@ static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
   if (mem == SEMB_DEVICE) return 0;
   SEMB_CUDA(cudaMemcpyAsync(dst, s.dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_ll_error(c);
 }
 
 // rmult = 1 / gs(ones)   (sempy/mesh.py:440-442); across ranks when a halo is set
@@ -317,6 +329,7 @@ static int build_rmult(semb_ctx* c) {
   reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->mult, c->n);
   SEMB_CUDA(cudaGetLastError());
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  SEMB_TRY(check_ll_error(c));
   if (c->vec[4]) {  // cached Jacobi diagonal is stale
     cudaFree(c->vec[4]);
     c->vec[4] = nullptr;
@@ -417,6 +430,7 @@ int semb_destroy(semb_ctx* c) {
     if (r != c->rank && c->ll_peer[r]) cudaIpcCloseMemHandle(c->ll_peer[r]);
   cudaFree(c->ll_local);
   cudaFree(c->ll_peer_dev);
+  cudaFree(c->ll_error);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_if_done) cudaEventDestroy(c->ev_if_done);
@@ -437,7 +451,7 @@ int semb_synchronize(semb_ctx* c) {
   SEMB_CHECK(c != nullptr, "semb_synchronize: ctx is NULL");
   SEMB_TRY(bind_device(c));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_ll_error(c);
 }
 
 int semb_set_derivative(semb_ctx* c, const double* D) {
@@ -817,7 +831,14 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   int chunk = 1;
   while (true) {
     SEMB_CUDA(cudaMemcpyAsync(c->h_pinned, &s->niter, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    c->h_pinned[2] = 0;
+    if (c->p2p && c->ll_error)
+      SEMB_CUDA(cudaMemcpyAsync(c->h_pinned + 2, c->ll_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SEMB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[2]) {
+      set_error("peer-memory exchange timed out: a neighbouring rank did not deliver (rank failure or table mismatch)");
+      return 4;
+    }
     if (c->h_pinned[1] || issued >= maxit) break;
     const int todo = std::min(chunk, maxit - issued);
     for (int it = 0; it < todo; ++it) {
@@ -832,7 +853,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         c->seq_scalar++;
         c->launch_count++;
         reduce_allreduce_kernel<false><<<1, RED_NT, 0, c->stream>>>(c->partials, np, &s->pAp, s, hist, c->ll_peer_dev,
-                                                                    c->rank, c->nranks, c->seq_scalar);
+                                                                    c->rank, c->nranks, c->seq_scalar, c->ll_error);
         SEMB_CUDA(cudaGetLastError());
         c->seq_halo++;
         SEMB_TRY(halo_gather(c, Ap, c->stream, done));
@@ -874,7 +895,8 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         c->seq_scalar++;
         c->launch_count++;
         reduce_allreduce_kernel<true><<<1, RED_NT, 0, c->stream>>>(c->partials, grid, &s->rdotr_new, s, hist,
-                                                                   c->ll_peer_dev, c->rank, c->nranks, c->seq_scalar);
+                                                                   c->ll_peer_dev, c->rank, c->nranks, c->seq_scalar,
+                                                                   c->ll_error);
       } else if (c->comm != nullptr && c->nranks > 1) {
         SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
         SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
@@ -903,7 +925,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   if (mem == SEMB_HOST)
     SEMB_CUDA(cudaMemcpyAsync(x, xdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_ll_error(c);
 }
 
 int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_apply_fn Minv, void* Minv_user,
@@ -1052,13 +1074,19 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
   return build_rmult(c);  // multiplicities now count the copies on the other ranks too
 }
 
-int semb_p2p_alloc(semb_ctx* c, char* handle64) {
+int semb_p2p_alloc(semb_ctx* c, int64_t halo_capacity, char* handle64) {
   SEMB_CHECK(c && handle64, "semb_p2p_alloc: NULL argument");
+  SEMB_CHECK(halo_capacity >= c->n_send, "semb_p2p_alloc: halo_capacity must cover this rank's interface entries");
   SEMB_CHECK(c->comm != nullptr && c->have_halo, "semb_p2p_alloc: call semb_comm_init and semb_set_halo first");
   SEMB_CHECK(c->nranks <= LL_MAXR, "semb_p2p_alloc: more ranks than the peer-memory path supports");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   SEMB_TRY(bind_device(c));
-  c->ll_halo_cap = std::max<int64_t>(c->n_send, 1);
+  // the same capacity on every rank: writers compute the parity offset inside the READER's region
+  c->ll_halo_cap = std::max<int64_t>(halo_capacity, 1);
+  if (c->ll_error == nullptr) {
+    SEMB_CUDA(cudaMalloc(&c->ll_error, sizeof(int)));
+    SEMB_CUDA(cudaMemset(c->ll_error, 0, sizeof(int)));
+  }
   const size_t words = (size_t)LL_SCALAR_WORDS + 2 * 2 * (size_t)c->ll_halo_cap;
   if (c->ll_local == nullptr) {
     SEMB_CUDA(cudaMalloc(&c->ll_local, words * sizeof(unsigned long long)));

@@ -128,14 +128,31 @@ __device__ __forceinline__ void ll_store(unsigned long long* dst, double v, unsi
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(lo), "r"(seq) : "memory");
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 1), "r"(hi), "r"(seq) : "memory");
 }
-__device__ __forceinline__ double ll_load(const unsigned long long* src, unsigned int seq) {
-  unsigned int lo, hi, f0, f1;
-  do {
+// A peer that died (or a table bug) must not hang the GPU: after LL_TIMEOUT_NS without the expected
+// sequence number the wait gives up, raises *ll_error and yields NaN; the host turns that into an error.
+constexpr unsigned long long LL_TIMEOUT_NS = 5000000000ull;
+__device__ __forceinline__ unsigned long long ll_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* src, unsigned int seq, int* ll_error) {
+  unsigned int lo = 0, hi = 0, f0, f1;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  while (true) {
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(f0) : "l"(src) : "memory");
-  } while (f0 != seq);
-  do {
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(f1) : "l"(src + 1) : "memory");
-  } while (f1 != seq);
+    if (f0 == seq && f1 == seq) break;
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = ll_now();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > LL_TIMEOUT_NS || *(volatile int*)ll_error) {
+        *(volatile int*)ll_error = 1;
+        return __longlong_as_double(0x7ff8000000000000ll);
+      }
+    }
+  }
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
@@ -143,7 +160,7 @@ __device__ __forceinline__ double ll_load(const unsigned long long* src, unsigne
 // result is bitwise identical everywhere.  Runs on the first LL_MAXR*LL_MAXV threads of one CTA
 // (all threads of the CTA must call it).
 __device__ __forceinline__ void ll_allreduce_cta(double* vals, int count, unsigned long long* const* __restrict__ peers,
-                                                 int rank, int nranks, unsigned int seq) {
+                                                 int rank, int nranks, unsigned int seq, int* ll_error) {
   __shared__ double s_v[LL_MAXR][LL_MAXV];
   const int r = threadIdx.x / LL_MAXV, cidx = threadIdx.x % LL_MAXV;
   const int64_t slot = (int64_t)(seq & 1) * (LL_MAXR * LL_MAXV * 2);
@@ -151,7 +168,7 @@ __device__ __forceinline__ void ll_allreduce_cta(double* vals, int count, unsign
   if (mine) {
     // my value cidx -> rank r's region, slot [parity][my rank][cidx]
     ll_store(peers[r] + slot + ((int64_t)rank * LL_MAXV + cidx) * 2, vals[cidx], seq);
-    s_v[r][cidx] = ll_load(peers[rank] + slot + ((int64_t)r * LL_MAXV + cidx) * 2, seq);
+    s_v[r][cidx] = ll_load(peers[rank] + slot + ((int64_t)r * LL_MAXV + cidx) * 2, seq, ll_error);
   }
   __syncthreads();
   if (threadIdx.x < count) {
@@ -163,8 +180,8 @@ __device__ __forceinline__ void ll_allreduce_cta(double* vals, int count, unsign
 }
 __global__ void __launch_bounds__(LL_MAXR* LL_MAXV)
 ll_allreduce_kernel(double* vals, int count, unsigned long long* const* __restrict__ peers, int rank, int nranks,
-                    unsigned int seq) {
-  ll_allreduce_cta(vals, count, peers, rank, nranks, seq);
+                    unsigned int seq, int* ll_error) {
+  ll_allreduce_cta(vals, count, peers, rank, nranks, seq, ll_error);
 }
 
 // halo_gather + remote write: the partial sum of send entry t goes to hbuf[t] (own use) and, as LL
@@ -192,14 +209,14 @@ __global__ void __launch_bounds__(VEC_NT)
 halo_scatter_p2p_kernel(double* __restrict__ x, const double* __restrict__ hbuf, const unsigned long long* __restrict__ ll_halo,
                         int64_t n_send, const int64_t* __restrict__ src_start, const int32_t* __restrict__ src_off,
                         const int64_t* __restrict__ copy_start, const int32_t* __restrict__ copy_ids, int64_t n_if,
-                        int64_t halo_cap, unsigned int seq, const int* __restrict__ done) {
+                        int64_t halo_cap, unsigned int seq, const int* __restrict__ done, int* ll_error) {
   if (done != nullptr && *done) return;
   const unsigned long long* base = ll_halo + (int64_t)(seq & 1) * halo_cap * 2;
   for (int64_t i = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; i < n_if; i += (int64_t)gridDim.x * VEC_NT) {
     double s = 0.0;
     for (int64_t q = src_start[i]; q < src_start[i + 1]; ++q) {
       const int64_t off = src_off[q];
-      s += off < n_send ? hbuf[off] : ll_load(base + (off - n_send) * 2, seq);
+      s += off < n_send ? hbuf[off] : ll_load(base + (off - n_send) * 2, seq, ll_error);
     }
     for (int64_t q = copy_start[i]; q < copy_start[i + 1]; ++q) x[copy_ids[q]] = s;
   }
@@ -443,7 +460,8 @@ reduce_and_step_kernel(const double* __restrict__ partials, int64_t n, CgScalars
 template <bool STEP>
 __global__ void __launch_bounds__(RED_NT)
 reduce_allreduce_kernel(const double* __restrict__ partials, int64_t n, double* out, CgScalars* s, double* hist,
-                        unsigned long long* const* __restrict__ peers, int rank, int nranks, unsigned int seq) {
+                        unsigned long long* const* __restrict__ peers, int rank, int nranks, unsigned int seq,
+                        int* ll_error) {
   __shared__ double s_red[RED_NT / 32];
   double v0 = 0.0, v1 = 0.0;
   int64_t t = threadIdx.x;
@@ -464,7 +482,7 @@ reduce_allreduce_kernel(const double* __restrict__ partials, int64_t n, double* 
     if (threadIdx.x == 0) *out = w;
   }
   __syncthreads();
-  ll_allreduce_cta(out, 1, peers, rank, nranks, seq);
+  ll_allreduce_cta(out, 1, peers, rank, nranks, seq, ll_error);
   if (STEP && threadIdx.x == 0 && !s->done) cg_step_scalars(s, hist);
 }
 

@@ -390,7 +390,8 @@ class Mesh:
         if os.environ.get("SEMB_P2P", "1") != "0" and not getattr(ctx, "p2p_ready", False):
             # peer-memory transport: publish this rank's receive region, map everybody else's
             handle = C.create_string_buffer(64)
-            _capi.check(lib.semb_p2p_alloc(ctx.handle, handle))
+            cap = max(self.comm.allgather(int(keep[3].size and h["send_start"].size - 1)))
+            _capi.check(lib.semb_p2p_alloc(ctx.handle, cap, handle))
             everyone = self.comm.allgather((bytes(handle.raw), [int(q) for q in h["nb_rank"]],
                                             [int(n) for n in h["nb_count"]]))
             me = self.comm.rank

@@ -71,11 +71,15 @@ def _worker(rank, size, port, dims, perturb, N, out):
         xo, ito = so.elliptic_cg(axo, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
         xg, itg = elliptic_cg(m, take(b), tol=1e-10, maxit=3000)
         errs["cg_iters"] = float(abs(itg - ito))
+        if itg != ito:
+            xg, _ = elliptic_cg(m, take(b), tol=0.0, maxit=ito)
         errs["cg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
         dinv = mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
         xo, ito = so.elliptic_pcg_jacobi(axo, dinv, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
         xg, itg = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
         errs["pcg_iters"] = float(abs(itg - ito))
+        if itg != ito:
+            xg, _ = elliptic_pcg(m, take(b), tol=0.0, maxit=ito)
         errs["pcg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
         res = comm.allgather(errs)
         if rank == 0:
@@ -87,17 +91,32 @@ def _worker(rank, size, port, dims, perturb, N, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dims,perturb,N", [((3, 3, 4), 0.3, 7), ((4, 3, 5), 0.2, 4)])
-def test_two_rank_solver_matches_oracle(dims, perturb, N, tmp_path):
-    if _ndev() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run(size, dims, perturb, N, tmp_path):
     import json
 
     import torch.multiprocessing as mp
 
     out = str(tmp_path / "res.json")
-    mp.spawn(_worker, args=(2, _free_port(), dims, perturb, N, out), nprocs=2, join=True)
-    for e in json.load(open(out)):
+    mp.spawn(_worker, args=(size, _free_port(), dims, perturb, N, out), nprocs=size, join=True)
+    return json.load(open(out))
+
+
+def test_four_rank_solver_matches_oracle(tmp_path):
+    """Middle ranks have two neighbours (two blocks in the exchange buffers)."""
+    if _ndev() < 4:
+        pytest.skip("needs 4 GPUs")
+    for e in _run(4, (3, 3, 8), 0.3, 7, tmp_path):
+        assert e["rmult"] == 0.0 and e["mask"] == 0.0
+        assert e["dssum"] < 1e-15 and e["ax_full"] <= 1e-12
+        assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
+        assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
+
+
+@pytest.mark.parametrize("dims,perturb,N", [((3, 3, 4), 0.3, 7), ((4, 3, 5), 0.2, 4)])
+def test_two_rank_solver_matches_oracle(dims, perturb, N, tmp_path):
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    for e in _run(2, dims, perturb, N, tmp_path):
         assert e["rmult"] == 0.0 and e["mask"] == 0.0
         assert e["dssum"] < 1e-15 and e["ax_full"] <= 1e-12
         assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
