@@ -8,6 +8,7 @@
 #include <utility>
 
 #include "ax_kernels.cuh"
+#include "axl_kernels.cuh"
 #include "common.cuh"
 #include "vec_kernels.cuh"
 
@@ -20,6 +21,10 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 // SEMB_AX_L2_PREFETCH=0 or semb_set_tuning("ax_l2_prefetch", 0) turns it off
 static int g_p2p_on = [] {  // 0: NCCL for the halo exchange and the scalar all-reduces (A/B against the peer-memory path)
   const char* v = getenv("SEMB_P2P");
+  return v ? atoi(v) : 1;
+}();
+static int g_ax_tuned_high_order = [] {  // 0: plane-sweep kernel for every order but N = 7 (A/B)
+  const char* v = getenv("SEMB_AX_TUNED_HIGH_ORDER");
   return v ? atoi(v) : 1;
 }();
 static int g_ax_l2_prefetch = [] {
@@ -113,6 +118,36 @@ static int launch_ax_generic(semb_ctx* c, const double* p, double* ap, bool mask
   return 0;
 }
 
+// K1 for Nq = 9..16 (axl_kernels.cuh): one CTA per element
+template <int NQ>
+static int launch_axl(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
+                      const int* done, int64_t part_off) {
+  using Cfg = AxlCfg<NQ>;
+  static bool attr_done[64] = {false};
+  DMatL<NQ> dl;
+  for (int q = 0; q < 5; ++q)
+    for (int r = 0; r < NQ; ++r) std::memcpy(&dl.d[q][r * NQ], &c->D.d[r * NQ], sizeof(double) * NQ);
+  if (!attr_done[c->device & 63]) {
+#define SEMB_ATTR(M, DT)                                                                                                  \
+  SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, M, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); \
+  SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, M, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SEMB_ATTR(true, true) SEMB_ATTR(true, false) SEMB_ATTR(false, true) SEMB_ATTR(false, false)
+#undef SEMB_ATTR
+    attr_done[c->device & 63] = true;
+  }
+  const unsigned grid = (unsigned)(e1 - e0);
+#define SEMB_LAUNCH_L(M, DT)                                                                                     \
+  axl_kernel<NQ, M, DT><<<grid, Cfg::NT, Cfg::SMEM, c->stream>>>(p, c->G6, ap, c->maskbits, c->partials + part_off, e0, dl, \
+                                                                done, g_ax_l2_prefetch)
+  if (mask && dot) SEMB_LAUNCH_L(true, true);
+  else if (mask) SEMB_LAUNCH_L(true, false);
+  else if (dot) SEMB_LAUNCH_L(false, true);
+  else SEMB_LAUNCH_L(false, false);
+#undef SEMB_LAUNCH_L
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Number of per-CTA dot partials the Ax launch over [e0,e1) writes.
 static int64_t ax_num_partials(const semb_ctx* c, int64_t e0, int64_t e1) {
   if (c->Nq == 8) return (e1 - e0 + AX8_WARPS - 1) / AX8_WARPS;
@@ -147,6 +182,11 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 #undef SEMB_LAUNCH_8
     SEMB_CUDA(cudaGetLastError());
     return 0;
+  }
+  if (g_ax_tuned_high_order) {
+    // the reference's test order (N = 10) and BASELINE config 3 (N = 15) get the tuned kernel
+    if (c->Nq == 16) return launch_axl<16>(c, p, ap, mask, dot, e0, e1, done, part_off);
+    if (c->Nq == 11) return launch_axl<11>(c, p, ap, mask, dot, e0, e1, done, part_off);
   }
   switch (c->Nq) {
 #define SEMB_CASE(Q) \
@@ -1189,6 +1229,10 @@ int semb_set_tuning(const char* name, int value) {
   SEMB_CHECK(name != nullptr, "semb_set_tuning: NULL name");
   if (std::strcmp(name, "ax_l2_prefetch") == 0) {
     g_ax_l2_prefetch = value;
+    return 0;
+  }
+  if (std::strcmp(name, "ax_tuned_high_order") == 0) {
+    g_ax_tuned_high_order = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {
