@@ -11,7 +11,7 @@ second with everything resident in HBM; ``e2e`` is the same solve called through
 the drop-in API with HOST (pinned) NumPy buffers, host<->device copies timed.
 ``roofline`` describes the dominant kernel (the fused Ax), timed live with CUDA
 events inside the timed region.  ``--impl reference`` times the CPU oracle (a
-NumPy restatement of the reference's algorithm) on a bounded sample.
+C/OpenMP restatement of the reference's algorithm, all host cores) on a bounded sample.
 """
 
 from __future__ import annotations
@@ -152,57 +152,61 @@ def build_problem(nel, perturb=0.0, comm=None):
     return m, b
 
 
-def oracle_problem(nel):
-    """Same problem for the CPU oracle (its own arrays; set-up through the
-    product's mesh class, which is input preparation, not the timed path)."""
+def oracle_problem(mesh, b):
+    """Arrays of the SAME problem for the CPU oracle (the mesh set-up is input preparation, done once
+    through the product's mesh class; the timed CPU path is the oracle's)."""
     from sempy_b200.derivative import reference_derivative_matrix
 
-    m, b = build_problem(nel)
     D = np.ascontiguousarray(reference_derivative_matrix(N_ORDER))
-    geom = m.get_geom()
-    g2l, gs = m.get_global_to_local_map()
-    return dict(geom=geom, D=D, g2l=g2l, gs=gs, rmult=m.get_rmult().copy(), mask=m.mask.copy(), b=b.copy(),
-                dof=m.get_num_elems() * m.Np)
+    g2l, gs = mesh.get_global_to_local_map()
+    return dict(geom=np.ascontiguousarray(mesh.get_geom()), D=D, g2l=g2l, gs=gs, rmult=mesh.get_rmult().copy(),
+                mask=mesh.mask.copy(), b=np.array(b, copy=True), dof=mesh.get_num_elems() * mesh.Np)
+
+
+CPU_ITERS = 10  # PCG iterations per CPU step: a bounded sample of the ~45-iteration solve
 
 
 def time_oracle(prob, iters, steps, warmup):
-    """Oracle Jacobi-PCG with a fixed iteration count per step; GDOF/s."""
+    """C/OpenMP oracle (oracle/c/sem_oracle.c), Jacobi-PCG with a fixed iteration count per step on all
+    host threads; returns (GDOF/s, ms per step, threads)."""
+    from oracle import c_oracle as co
     from oracle import sem_oracle as so
 
     geom, D = prob["geom"], prob["D"]
-    axo = lambda v: so.elliptic_ax_batched(geom, v, N_ORDER, D)
     diag = so.gather_scatter(so.jacobi_diagonal(geom, N_ORDER, D), prob["g2l"], prob["gs"])
     dinv = prob["mask"] / diag
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        _, it = so.elliptic_pcg_jacobi(axo, dinv, prob["mask"], prob["g2l"], prob["gs"], prob["rmult"], prob["b"], tol=1e-30, maxit=iters)
+        _, it = co.cg(geom, N_ORDER, D, prob["mask"], prob["g2l"], prob["gs"], prob["rmult"], prob["b"], 1e-30, iters, dinv=dinv)
         t1 = time.perf_counter()
         assert it == iters
         if s >= warmup:
             times.append(t1 - t0)
     total = sum(times)
-    return prob["dof"] * iters * steps / total / 1e9, total / steps * 1e3
+    return prob["dof"] * iters * steps / total / 1e9, total / steps * 1e3, co.num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nel, iters = 10, 5
-    prob = oracle_problem(nel)
-    val, ms = time_oracle(prob, iters, args.steps, min(args.warmup, 1))
-    cores = os.cpu_count()
+    mesh, b = build_problem(args.nel, args.perturb)
+    prob = oracle_problem(mesh, b)
+    warm = min(args.warmup, 1)
+    val, ms, threads = time_oracle(prob, CPU_ITERS, args.steps, warm)
+    sample = (f"C/OpenMP restatement of the reference algorithm (oracle/c/sem_oracle.c), {threads} threads, Jacobi-PCG on the "
+              f"full {args.nel}^3-element N={N_ORDER} mesh, {CPU_ITERS} iterations per step x {args.steps} steps")
     line = {
-        "impl": "reference", "metric": "FP64 Jacobi-PCG Poisson throughput, N=7 (local DOF x iterations / s)",
-        "value": val, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": f"FP64 Jacobi-PCG Poisson throughput, N={N_ORDER} (local DOF x iterations / s)",
+        "value": val, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "3D Poisson, straight box 32^3 elements, N=7, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
-                   "sample": f"{nel}^3 elements, {iters} PCG iterations per step"},
-        "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle (NumPy restatement, batched matmul Ax, BLAS threads = host default) Jacobi-PCG, "
-                                   f"{nel}^3 elements N=7, {iters} iterations x {args.steps} steps"},
+        "config": {"workload": f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {args.nel}^3 elements, N={N_ORDER}, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
+                   "sample": f"{CPU_ITERS} PCG iterations per step on the full mesh",
+                   "note": "the reference is pure Python (~1 MDOF/s, one core) and cannot be shipped to the GPU box; "
+                           "this arm times its C/OpenMP restatement on all host cores"},
+        "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -366,22 +370,24 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1:
         t_cpu0 = time.perf_counter()
-        prob = oracle_problem(10)
-        cpu_val, _ = time_oracle(prob, 5, 2, 1)
+        prob = oracle_problem(mesh, b_host)
+        cpu_val, _, threads = time_oracle(prob, CPU_ITERS, 2, 1)
         cpu_secs = time.perf_counter() - t_cpu0
-        cpu_baseline = {"value": cpu_val, "unit": "GDOF/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": "oracle (NumPy restatement, batched matmul Ax) Jacobi-PCG, 10^3 elements N=7, "
-                                  "5 iterations x 2 steps (%.0f s incl. set-up)" % cpu_secs}
+        cpu_baseline = {"value": cpu_val, "unit": "GDOF/s", "cores": threads, "kind": "port",
+                        "sample": "C/OpenMP restatement of the reference algorithm (oracle/c/sem_oracle.c), %d threads, "
+                                  "Jacobi-PCG on the same full mesh, %d iterations x 2 steps (%.0f s); the Python "
+                                  "reference itself runs ~1 MDOF/s on one core (BASELINE.md)" % (threads, CPU_ITERS, cpu_secs)}
+        del prob
     if world == 1:
-        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {nel}^3 elements, N=7, "
+        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {nel}^3 elements, N={N_ORDER}, "
                     "Jacobi-PCG tol 1e-8 (BASELINE config 2)")
     else:
         workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {2 * nel}x{2 * nel}x{(nel // 4) * world} "
-                    f"elements in z-slabs of {nel ** 3} elements per GPU, N=7, Jacobi-PCG tol 1e-8 "
+                    f"elements in z-slabs of {nel ** 3} elements per GPU, N={N_ORDER}, Jacobi-PCG tol 1e-8 "
                     "(weak scaling of BASELINE config 2; the 8-GPU mesh is the 64^3 box of config 4)")
 
     line = {
-        "metric": "FP64 Jacobi-PCG Poisson throughput, N=7 (local DOF x iterations / s)",
+        "metric": f"FP64 Jacobi-PCG Poisson throughput, N={N_ORDER} (local DOF x iterations / s)",
         "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -394,9 +400,9 @@ def run_ours(args):
         "cg_iters_per_s": iters_total / (ms_total * 1e-3),
         "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + BYTES_GS, "achieved_gbs": axgs_gbs,
                   "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
-        "roofline": {"bound": "hbm", "kernel": "ax8_kernel (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": ("ax8_kernel" if N_ORDER == 7 else "axl_kernel" if N_ORDER >= 8 else "ax_generic_kernel") + " (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
                      "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak,
-                     "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if world == 1 and nel == 32 else None,
+                     "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if world == 1 and nel == 32 and N_ORDER == 7 else None,
                      "traffic_source": (ncu_traffic() or {}).get("source"), "algorithmic_bytes_per_launch": BYTES_AX * dof,
                      "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "avg_ms_is": "per CG iteration", "launches_timed": kern["ax"][1],
                      "share_of_step": kern["ax"][0] / ms_total, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
@@ -422,7 +428,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2)")
     ap.add_argument("--perturb", type=float, default=0.0, help="vertex displacement in units of h (0.3 = the deformed mesh of config 4)")
+    ap.add_argument("--order", type=int, default=7, help="polynomial order N (BASELINE config 3: --order 15 --nel 16 or 32)")
     args = ap.parse_args()
+    global N_ORDER, NQ, F_SHARED, BYTES_GS
+    N_ORDER, NQ = args.order, args.order + 1
+    F_SHARED = 1.0 - ((N_ORDER - 1) / (N_ORDER + 1)) ** 3
+    BYTES_GS = 20.0 * F_SHARED
     if args.impl == "reference":
         run_reference(args)
     else:

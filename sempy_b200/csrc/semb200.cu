@@ -184,9 +184,17 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
     return 0;
   }
   if (g_ax_tuned_high_order) {
-    // the reference's test order (N = 10) and BASELINE config 3 (N = 15) get the tuned kernel
-    if (c->Nq == 16) return launch_axl<16>(c, p, ap, mask, dot, e0, e1, done, part_off);
-    if (c->Nq == 11) return launch_axl<11>(c, p, ap, mask, dot, e0, e1, done, part_off);
+    // N = 8 ... 15 (the reference's test order N = 10, BASELINE config 3 at N = 15): tuned kernel
+    switch (c->Nq) {
+#define SEMB_CASE_L(Q) \
+  case Q:              \
+    return launch_axl<Q>(c, p, ap, mask, dot, e0, e1, done, part_off);
+      SEMB_CASE_L(9) SEMB_CASE_L(10) SEMB_CASE_L(11) SEMB_CASE_L(12) SEMB_CASE_L(13) SEMB_CASE_L(14) SEMB_CASE_L(15)
+      SEMB_CASE_L(16)
+#undef SEMB_CASE_L
+      default:
+        break;
+    }
   }
   switch (c->Nq) {
 #define SEMB_CASE(Q) \
