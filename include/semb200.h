@@ -103,6 +103,22 @@ int semb_gradient_transpose(int device, int Nq, const double* D, int64_t nelem, 
 int semb_kron(int device, const double* Sz, int nz, int mz, const double* Sy, int ny, int my, const double* Sx,
               int nx, int mx, int64_t nelem, const double* U, double* out, int mem);
 
+/* ---- mesh set-up on the device (inputs of the path) -------------------------
+ * Global numbering of n local nodes by coordinate, the rule of
+ * Mesh.establish_global_numbering (sempy/mesh.py:389-435): stable lexicographic
+ * sort by exact (x, y, z), a new id whenever the SQUARED distance to the next
+ * sorted point exceeds tol2 (the reference uses 1e-12), ids from 1.  Outputs:
+ * gid int32[n] (mesh.global_id), g2l int64[n] (global_to_local), gstart
+ * int64[<= n+1] (global_start, *nglobal + 1 entries).  Bit-identical to the
+ * reference's Python sort for the same coordinates. */
+int semb_numbering(int device, int64_t n, const double* x, const double* y, const double* z, double tol2, int32_t* gid,
+                   int64_t* g2l, int64_t* gstart, int64_t* nglobal, int mem);
+/* Geometric factors of Mesh.calc_geometric_factors (sempy/mesh.py:304-356) for
+ * nelem elements: G6 (nelem,6,Np) = (grad a . grad b) * B * J with B the tensor
+ * product of the GLL weights w[Nq], and (optional) the Jacobian (nelem,Np). */
+int semb_geom_factors(int device, int Nq, const double* D, const double* w, int64_t nelem, const double* xe,
+                      const double* ye, const double* ze, double* G6, double* jaco, int mem);
+
 /* ---- solvers ------------------------------------------------------------
  * elliptic_cg(mesh, b, tol, maxit, verbose), sempy/elliptic.py:30-73, run
  * entirely on the device: weighted dots, pAp before the gather-scatter, stop
@@ -157,7 +173,7 @@ int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* 
  * layout (= the sum of q's nb_count over q's neighbours listed before this rank), and hands both to
  * semb_p2p_attach.  From then on the halo exchange is written straight into the neighbour's memory by
  * the gather kernel and the CG dots are summed by a one-CTA peer-memory all-reduce; NCCL stays as the
- * fallback (semb_set_tuning("p2p", 0)).  A wait for a peer gives up after 5 s: the call that
+ * fallback (semb_set_tuning("p2p", 0)).  A wait for a peer gives up after 60 s: the call that
  * synchronises next returns an error instead of hanging the GPU. */
 int semb_p2p_alloc(semb_ctx* ctx, int64_t halo_capacity, char* handle64);
 int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv_off);

@@ -50,6 +50,16 @@ SIGNATURES = {
         [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
          C.c_int64, C.c_void_p, C.c_void_p, C.c_int],
     ),
+    "semb_numbering": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.POINTER(C.c_int64), C.c_int],
+    ),
+    "semb_geom_factors": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int],
+    ),
     "semb_cg": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p],

@@ -10,6 +10,7 @@
 #include "ax_kernels.cuh"
 #include "axl_kernels.cuh"
 #include "common.cuh"
+#include "setup_kernels.cuh"
 #include "vec_kernels.cuh"
 
 namespace semb {
@@ -825,6 +826,100 @@ int semb_kron(int device, const double* Sz, int nz, int mz, const double* Sy, in
   SEMB_CUDA(cudaGetLastError());
   SEMB_CUDA(cudaDeviceSynchronize());
   SEMB_TRY(o.out(out, mem, (size_t)nelem * nout));
+  return 0;
+}
+
+// ---- mesh set-up on the device ---------------------------------------------------
+int semb_numbering(int device, int64_t n, const double* x, const double* y, const double* z, double tol2, int32_t* gid,
+                   int64_t* g2l, int64_t* gstart, int64_t* nglobal, int mem) {
+  SEMB_CHECK(n > 0 && x && y && z && gid && g2l && gstart && nglobal, "semb_numbering: bad argument");
+  SEMB_CHECK(n < (int64_t)2147483647, "semb_numbering: more than 2^31 nodes");
+  SEMB_CUDA(cudaSetDevice(device));
+  TmpBuf bx, by, bz;
+  SEMB_TRY(bx.in(x, mem, (size_t)n, true));
+  SEMB_TRY(by.in(y, mem, (size_t)n, true));
+  SEMB_TRY(bz.in(z, mem, (size_t)n, true));
+  struct Dev {
+    void* p = nullptr;
+    ~Dev() { cudaFree(p); }
+    int alloc(size_t bytes) {
+      SEMB_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+      return 0;
+    }
+  } k0, k1, i0, i1, fl, sc, st, tmp, cnt;
+  SEMB_TRY(k0.alloc(8 * (size_t)n));
+  SEMB_TRY(k1.alloc(8 * (size_t)n));
+  SEMB_TRY(i0.alloc(8 * (size_t)n));
+  SEMB_TRY(i1.alloc(8 * (size_t)n));
+  unsigned long long* keys[2] = {(unsigned long long*)k0.p, (unsigned long long*)k1.p};
+  int64_t* idx[2] = {(int64_t*)i0.p, (int64_t*)i1.p};
+  const int grid = vec_grid(n);
+  iota_kernel<<<grid, VEC_NT>>>(idx[0], n);
+  size_t tmp_bytes = 0;
+  SEMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys[0], keys[1], idx[0], idx[1], (int)n));
+  size_t scan_bytes = 0, sel_bytes = 0;
+  SEMB_TRY(fl.alloc(4 * (size_t)n));
+  SEMB_TRY(sc.alloc(4 * (size_t)n));
+  SEMB_TRY(st.alloc(8 * ((size_t)n + 1)));
+  SEMB_TRY(cnt.alloc(8));
+  SEMB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)fl.p, (int*)sc.p, (int)n));
+  SEMB_CUDA(cub::DeviceSelect::Flagged(nullptr, sel_bytes, idx[1], (int*)fl.p, (int64_t*)st.p, (int64_t*)cnt.p, (int)n));
+  SEMB_TRY(tmp.alloc(std::max(tmp_bytes, std::max(scan_bytes, sel_bytes))));
+  size_t tb = std::max(tmp_bytes, std::max(scan_bytes, sel_bytes));
+  // least-significant key first: z, then y, then x (radix sort is stable) == np.lexsort((z, y, x))
+  const double* coord[3] = {bz.dev, by.dev, bx.dev};
+  int cur = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    make_keys_kernel<<<grid, VEC_NT>>>(coord[pass], idx[cur], keys[0], n);
+    SEMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys[0], keys[1], idx[cur], idx[1 - cur], (int)n));
+    cur = 1 - cur;
+  }
+  const int64_t* order = idx[cur];
+  gap_flags_kernel<<<grid, VEC_NT>>>(bx.dev, by.dev, bz.dev, order, tol2, (int*)fl.p, n);
+  SEMB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, (int*)fl.p, (int*)sc.p, (int)n));
+  TmpBuf dummy;
+  // ids back in local order (int32), stored in the free key buffer
+  int32_t* gid_dev = (int32_t*)keys[0];
+  scatter_ids_kernel<<<grid, VEC_NT>>>(order, (int*)sc.p, gid_dev, n);
+  // segment starts: sorted positions whose flag is set
+  iota_kernel<<<grid, VEC_NT>>>(idx[1 - cur], n);
+  SEMB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, idx[1 - cur], (int*)fl.p, (int64_t*)st.p, (int64_t*)cnt.p, (int)n));
+  SEMB_CUDA(cudaGetLastError());
+  int64_t ng = 0;
+  SEMB_CUDA(cudaMemcpy(&ng, cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SEMB_CUDA(cudaMemcpy((int64_t*)st.p + ng, &n, sizeof(int64_t), cudaMemcpyHostToDevice));
+  const cudaMemcpyKind kind = mem == SEMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  SEMB_CUDA(cudaMemcpy(gid, gid_dev, sizeof(int32_t) * (size_t)n, kind));
+  SEMB_CUDA(cudaMemcpy(g2l, order, sizeof(int64_t) * (size_t)n, kind));
+  SEMB_CUDA(cudaMemcpy(gstart, st.p, sizeof(int64_t) * ((size_t)ng + 1), kind));
+  *nglobal = ng;
+  return 0;
+}
+
+int semb_geom_factors(int device, int Nq, const double* D, const double* w, int64_t nelem, const double* xe,
+                      const double* ye, const double* ze, double* G6, double* jaco, int mem) {
+  SEMB_CHECK(D && w && xe && ye && ze && G6 && nelem > 0, "semb_geom_factors: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  DMat dm, wm;
+  SEMB_TRY(make_dmat(dm, D, Nq));
+  std::memset(wm.d, 0, sizeof(wm.d));
+  std::memcpy(wm.d, w, sizeof(double) * Nq);
+  const size_t cnt = (size_t)nelem * Nq * Nq * Nq;
+  TmpBuf bx, by, bz, bg, bj;
+  SEMB_TRY(bx.in(xe, mem, cnt, true));
+  SEMB_TRY(by.in(ye, mem, cnt, true));
+  SEMB_TRY(bz.in(ze, mem, cnt, true));
+  SEMB_TRY(bg.in(G6, mem, 6 * cnt, false));
+  if (jaco) SEMB_TRY(bj.in(jaco, mem, cnt, false));
+  const int Np = Nq * Nq * Nq;
+  const size_t smem = sizeof(double) * 3 * Np;
+  SEMB_CUDA(cudaFuncSetAttribute(geom_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 4096)));
+  geom_factors_kernel<<<(unsigned)nelem, std::min(256, ((Np + 31) / 32) * 32), smem>>>(bx.dev, by.dev, bz.dev, bg.dev,
+                                                                                      jaco ? bj.dev : nullptr, Nq, dm, wm);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaDeviceSynchronize());
+  SEMB_TRY(bg.out(G6, mem, 6 * cnt));
+  if (jaco) SEMB_TRY(bj.out(jaco, mem, cnt));
   return 0;
 }
 

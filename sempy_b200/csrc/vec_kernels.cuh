@@ -130,7 +130,8 @@ __device__ __forceinline__ void ll_store(unsigned long long* dst, double v, unsi
 }
 // A peer that died (or a table bug) must not hang the GPU: after LL_TIMEOUT_NS without the expected
 // sequence number the wait gives up, raises *ll_error and yields NaN; the host turns that into an error.
-constexpr unsigned long long LL_TIMEOUT_NS = 5000000000ull;
+// The limit is generous because ranks legitimately drift apart by seconds during host-side mesh set-up.
+constexpr unsigned long long LL_TIMEOUT_NS = 60000000000ull;
 __device__ __forceinline__ unsigned long long ll_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

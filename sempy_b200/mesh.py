@@ -129,6 +129,28 @@ def global_numbering_from_coordinates(xe, ye, ze, tol=1e-12):
     return ids.reshape(E, Np), order, start
 
 
+def global_numbering_device(xe, ye, ze, tol=1e-12):
+    """Same rule, same outputs, computed on the GPU (semb_numbering: three stable radix-sort passes,
+    gap flags, prefix sum).  Bit-identical to ``global_numbering_from_coordinates``."""
+    lib = _capi.lib()
+    _capi.require_gpu()
+    E, Np = xe.shape
+    n = E * Np
+    x, y, z = (_capi.as_f64(c).reshape(-1) for c in (xe, ye, ze))
+    gid = np.empty(n, dtype=np.int32)
+    g2l = np.empty(n, dtype=np.int64)
+    start = np.empty(n + 1, dtype=np.int64)
+    ng = C.c_int64(0)
+    _capi.check(lib.semb_numbering(_capi.current_device(), n, x.ctypes.data, y.ctypes.data, z.ctypes.data, float(tol),
+                                   gid.ctypes.data, g2l.ctypes.data, start.ctypes.data, C.byref(ng), _capi.HOST))
+    return gid.reshape(E, Np), g2l, start[: ng.value + 1].copy()
+
+
+def device_setup_enabled():
+    """Mesh set-up (numbering, geometric factors) on the GPU instead of host NumPy: SEMB_DEVICE_SETUP=1."""
+    return os.environ.get("SEMB_DEVICE_SETUP", "0") == "1"
+
+
 def bounding_box_mask(xe, ye, ze, tol=1e-8, bbox=None):
     """0 where any coordinate is within ``tol`` of the global bounding box
     (homogeneous Dirichlet), else 1; sempy/mesh.py:449-477, flat (E*Np,).
@@ -276,6 +298,20 @@ class Mesh:
         coordinate derivatives come from the batched GPU gradient."""
         n = self.Nq
         D = reference_derivative_matrix(self.N)
+        if device_setup_enabled():
+            # one fused kernel: nine derivatives and the metric formulas per node (semb_geom_factors)
+            lib = _capi.lib()
+            E, Np = self.xe.shape
+            _, w = gauss_lobatto(self.N)
+            D, w = _capi.as_f64(D), _capi.as_f64(w)
+            g6 = np.empty((E, 6, Np))
+            J = np.empty((E, Np))
+            xe, ye, ze = (_capi.as_f64(c) for c in (self.xe, self.ye, self.ze))
+            _capi.check(lib.semb_geom_factors(_capi.current_device(), n, D.ctypes.data, w.ctypes.data, E, xe.ctypes.data,
+                                              ye.ctypes.data, ze.ctypes.data, g6.ctypes.data, J.ctypes.data, _capi.HOST))
+            self.geom6, self.jaco, self._B = g6, J, reference_mass_matrix_3d(self.N)
+            self._dirty["geom"] = True
+            return
         xr, xs, xt = gradient(self.xe, n, D)
         yr, ys, yt = gradient(self.ye, n, D)
         zr, zs, zt = gradient(self.ze, n, D)
@@ -316,9 +352,8 @@ class Mesh:
     def establish_global_numbering(self):
         """Global ids by coordinate sort (sempy/mesh.py:389-442); the gslib
         handle of the reference becomes the device gather-scatter schedule."""
-        self.global_id, self.global_to_local, self.global_start = global_numbering_from_coordinates(
-            self.xe, self.ye, self.ze
-        )
+        number = global_numbering_device if device_setup_enabled() else global_numbering_from_coordinates
+        self.global_id, self.global_to_local, self.global_start = number(self.xe, self.ye, self.ze)
         if self.comm.size > 1:
             # ids are local to the rank; nodes with copies on other ranks go into the halo tables
             cand = distributed.candidate_node_mask(self.elem_to_vert_map, self._shared_vertex, self.N)

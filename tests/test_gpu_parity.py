@@ -247,6 +247,64 @@ def test_generated_meshes_vs_oracle(dims, perturb, N):
     assert rel_inf(xg, xo) < 1e-10
 
 
+@pytest.mark.parametrize("case", MESH_CASES)
+def test_device_setup_matches_reference(case):
+    """semb_numbering is bit-exact against the reference's numbering on the reference's coordinates;
+    semb_geom_factors matches the reference's geometric factors to 1e-12."""
+    from sempy_b200 import _capi
+    from sempy_b200 import mesh as pm
+    from sempy_b200.quadrature import gauss_lobatto
+    import ctypes as C
+
+    g = load_golden(case)
+    gid, g2l, gs = pm.global_numbering_device(g["xe"], g["ye"], g["ze"])
+    assert gid.dtype == np.int32 and np.array_equal(gid, g["global_id"])
+    assert np.array_equal(g2l, g["global_to_local"]) and np.array_equal(gs, g["global_start"])
+    N = int(g["N"])
+    E, Np = g["xe"].shape
+    _, w = gauss_lobatto(N)
+    g6, J = np.empty((E, 6, Np)), np.empty((E, Np))
+    D = np.ascontiguousarray(g["D"])
+    _capi.check(_capi.lib().semb_geom_factors(0, N + 1, D.ctypes.data, w.ctypes.data, E, g["xe"].ctypes.data,
+                                              g["ye"].ctypes.data, g["ze"].ctypes.data, g6.ctypes.data, J.ctypes.data,
+                                              _capi.HOST))
+    assert np.max(np.abs(g6 - g["geom6"])) <= 1e-12 * np.abs(g["geom6"]).max()
+    assert np.allclose(J, g["jaco"], rtol=1e-11)
+
+
+def test_device_setup_large_and_signed_zero(monkeypatch):
+    """A generated 12^3, N=7 box (884 736 nodes) numbers identically on host and device, including
+    coordinates that are -0.0 on one copy and +0.0 on another; the whole set-up also runs with
+    SEMB_DEVICE_SETUP=1 and solves the same problem."""
+    from sempy_b200 import mesh as pm
+    from sempy_b200.elliptic import elliptic_pcg
+
+    m = pm.box_mesh(12, perturb=0.3, seed=3)
+    m.find_physical_coordinates(7)
+    xe, ye, ze = m.xe.copy(), m.ye.copy(), m.ze.copy()
+    xe[xe == 0.0] = np.where(np.arange((xe == 0.0).sum()) % 2 == 0, 0.0, -0.0)
+    h = pm.global_numbering_from_coordinates(xe, ye, ze)
+    d = pm.global_numbering_device(xe, ye, ze)
+    for a, b in zip(h, d):
+        assert np.array_equal(a, b)
+    sols = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SEMB_DEVICE_SETUP", flag)
+        mm = pm.box_mesh(6, perturb=0.3, seed=3)
+        mm.find_physical_coordinates(7)
+        mm.establish_global_numbering()
+        mm.calc_geometric_factors()
+        mm.setup_mask()
+        X, Y, Z = mm.get_x(), mm.get_y(), mm.get_z()
+        b = 3 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z) * mm.get_mass() * mm.get_jaco()
+        b = mm.apply_mask(mm.dssum(b))
+        x, it = elliptic_pcg(mm, b, tol=1e-10, maxit=2000)
+        sols.append((x, it, mm.global_id.copy(), mm.geom6.copy()))
+    assert np.array_equal(sols[0][2], sols[1][2])
+    assert np.max(np.abs(sols[0][3] - sols[1][3])) <= 1e-12 * np.abs(sols[0][3]).max()
+    assert abs(sols[0][1] - sols[1][1]) <= 1 and rel_inf(sols[1][0], sols[0][0]) < 1e-9
+
+
 @pytest.fixture(scope="module")
 def big_mesh():
     """BASELINE config 2 size: 32^3 elements, N=7 (16.8 M local nodes)."""
