@@ -147,8 +147,10 @@ def global_numbering_device(xe, ye, ze, tol=1e-12):
 
 
 def device_setup_enabled():
-    """Mesh set-up (numbering, geometric factors) on the GPU instead of host NumPy: SEMB_DEVICE_SETUP=1."""
-    return os.environ.get("SEMB_DEVICE_SETUP", "0") == "1"
+    """Numbering and geometric factors run on the GPU (semb_numbering, semb_geom_factors) unless
+    SEMB_DEVICE_SETUP=0 selects the vectorised host NumPy forms (same results: ids bit-identical,
+    factors to rounding)."""
+    return os.environ.get("SEMB_DEVICE_SETUP", "1") != "0"
 
 
 def bounding_box_mask(xe, ye, ze, tol=1e-8, bbox=None):
