@@ -213,16 +213,25 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 // ---- K2 dispatch -----------------------------------------------------------
 static int launch_gs(semb_ctx* c, double* x, const int* done) {
   ProfScope ps(c, SEMB_K_GS);
-  GsPlan plan{0, 0, 0, 0, 0, 0};
+  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
     if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
     else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
     else if (k.len == 8) { plan.n8 = k.nseg; plan.off8 = k.off; }
   }
-  const int64_t total = plan.n2 + plan.n4 + plan.n8;
-  if (total > 0) {
+  // blocks per class in proportion to their loads+stores; each thread takes 4 / 2 / 1 segments per trip
+  auto blocks_for = [](int64_t nseg, int per_thread) {
+    if (nseg == 0) return 0;
+    const int64_t want = (nseg + (int64_t)VEC_NT * per_thread - 1) / ((int64_t)VEC_NT * per_thread);
+    return (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8);
+  };
+  plan.b2 = blocks_for(plan.n2, 4);
+  plan.b4 = blocks_for(plan.n4, 2);
+  plan.b8 = blocks_for(plan.n8, 1);
+  const int total_blocks = plan.b2 + plan.b4 + plan.b8;
+  if (total_blocks > 0) {
     c->launch_count++;
-    gs_fixed_kernel<<<vec_grid(total), VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
+    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
     SEMB_CUDA(cudaGetLastError());
   }
   if (c->gs_var_nseg > 0) {

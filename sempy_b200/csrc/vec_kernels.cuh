@@ -19,8 +19,7 @@ constexpr int VEC_NT = 256;
 // back to every copy.  Traffic: 8 + 4 + 8 bytes per shared local node.
 // ---------------------------------------------------------------------------
 template <int L>
-__device__ __forceinline__ void gs_segment(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t s) {
-  int id[L];
+__device__ __forceinline__ void gs_load_ids(const int32_t* __restrict__ ids, int64_t s, int (&id)[L]) {
   if (L == 2) {
     const int2 v = __ldg(reinterpret_cast<const int2*>(ids) + s);
     id[0] = v.x;
@@ -35,35 +34,71 @@ __device__ __forceinline__ void gs_segment(double* __restrict__ x, const int32_t
       id[4 * c + 3] = v.w;
     }
   }
-  double v[L];
-#pragma unroll
-  for (int c = 0; c < L; ++c) v[c] = x[id[c]];
-  double sum = v[0];
-#pragma unroll
-  for (int c = 1; c < L; ++c) sum += v[c];
-#pragma unroll
-  for (int c = 0; c < L; ++c) x[id[c]] = sum;
 }
 
-// All fixed-length classes in ONE launch: thread t owns segment t of the
-// concatenation [len-2 | len-4 | len-8]; only the warps that straddle a class
-// boundary diverge.  (Three launches cost two extra drain/launch bubbles and a
-// nearly empty len-8 grid: 8.8 us for 0.13 waves, profiles/r01_ncu_summary.md.)
+// U segments per thread, all index loads first, then all gathers, then sums and stores: the pass is
+// latency-bound (ncu: 48 % DRAM at exactly the sector-level traffic), so memory-level parallelism per
+// thread is what counts.
+template <int L, int U>
+__device__ __forceinline__ void gs_segments(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t first,
+                                            int64_t stride, int64_t nseg) {
+  int id[U][L];
+  double v[U][L];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t s = first + u * stride;
+    if (s < nseg) gs_load_ids<L>(ids, s, id[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (first + u * stride < nseg) {
+#pragma unroll
+      for (int c = 0; c < L; ++c) v[u][c] = x[id[u][c]];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (first + u * stride < nseg) {
+      double sum = v[u][0];
+#pragma unroll
+      for (int c = 1; c < L; ++c) sum += v[u][c];
+#pragma unroll
+      for (int c = 0; c < L; ++c) x[id[u][c]] = sum;
+    }
+  }
+}
+
+// All fixed-length classes in ONE launch: the grid is split into three block ranges (len 2 | 4 | 8), so
+// a block works on one class only.  (Three launches cost two extra drain/launch bubbles and a nearly
+// empty len-8 grid: 8.8 us for 0.13 waves, profiles/r01_summary.md.)
 struct GsPlan {
-  int64_t n2, n4, n8;       // segments per class
-  int64_t off2, off4, off8; // start of each class in ids (multiples of 4 ints)
+  int64_t n2, n4, n8;        // segments per class
+  int64_t off2, off4, off8;  // start of each class in ids (multiples of 4 ints)
+  int b2, b4, b8;            // blocks per class
 };
 
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
                 const int* __restrict__ done) {
   if (done != nullptr && *done) return;
-  const int64_t total = plan.n2 + plan.n4 + plan.n8;
-  for (int64_t t = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * VEC_NT) {
-    if (t < plan.n2) gs_segment<2>(x, ids + plan.off2, t);
-    else if (t < plan.n2 + plan.n4) gs_segment<4>(x, ids + plan.off4, t - plan.n2);
-    else gs_segment<8>(x, ids + plan.off8, t - plan.n2 - plan.n4);
+  int b = blockIdx.x;
+  if (b < plan.b2) {
+    const int64_t stride = (int64_t)plan.b2 * VEC_NT;
+    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += 4 * stride)
+      gs_segments<2, 4>(x, ids + plan.off2, t, stride, plan.n2);
+    return;
   }
+  b -= plan.b2;
+  if (b < plan.b4) {
+    const int64_t stride = (int64_t)plan.b4 * VEC_NT;
+    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n4; t += 2 * stride)
+      gs_segments<4, 2>(x, ids + plan.off4, t, stride, plan.n4);
+    return;
+  }
+  b -= plan.b4;
+  const int64_t stride = (int64_t)plan.b8 * VEC_NT;
+  for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n8; t += stride)
+    gs_segments<8, 1>(x, ids + plan.off8, t, stride, plan.n8);
 }
 
 // Segments of any other length (unstructured meshes): CSR offsets.
