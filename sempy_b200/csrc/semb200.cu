@@ -211,9 +211,10 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 }
 
 // ---- K2 dispatch -----------------------------------------------------------
-static int launch_gs(semb_ctx* c, double* x, const int* done) {
+static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_src = nullptr, int64_t red_n = 0,
+                     double* red_out = nullptr) {
   ProfScope ps(c, SEMB_K_GS);
-  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
+  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0, red_src, red_n, red_out};
   for (const GsClass& k : c->gs_classes) {
     if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
     else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
@@ -228,7 +229,7 @@ static int launch_gs(semb_ctx* c, double* x, const int* done) {
   plan.b2 = blocks_for(plan.n2, 4);
   plan.b4 = blocks_for(plan.n4, 2);
   plan.b8 = blocks_for(plan.n8, 1);
-  const int total_blocks = plan.b2 + plan.b4 + plan.b8;
+  const int total_blocks = plan.b2 + plan.b4 + plan.b8 + (red_out != nullptr ? 1 : 0);
   if (total_blocks > 0) {
     c->launch_count++;
     gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
@@ -452,6 +453,8 @@ int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq) {
   SEMB_CUDA(cudaMalloc(&c->scal, sizeof(CgScalars) + 8 * sizeof(double)));
   SEMB_CUDA(cudaMemset(c->scal, 0, sizeof(CgScalars) + 8 * sizeof(double)));
   SEMB_CUDA(cudaMallocHost(&c->h_pinned, 64));
+  SEMB_CUDA(cudaMalloc(&c->ticket, 4 * sizeof(unsigned int)));
+  SEMB_CUDA(cudaMemset(c->ticket, 0, 4 * sizeof(unsigned int)));
   if (ensure_partials(c)) return 1;
   *out = c;
   return 0;
@@ -470,6 +473,7 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->mask_ids);
   cudaFree(c->partials);
   cudaFree(c->scal);
+  cudaFree(c->ticket);
   cudaFree(c->hist);
   for (double* v : c->vec) cudaFree(v);
   cudaFreeHost(c->h_pinned);
@@ -979,6 +983,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   SEMB_CUDA(cudaGetLastError());
 
   const int* done = &s->done;
+  const bool multi = c->comm != nullptr && c->nranks > 1;
   int issued = 0;
   int chunk = 1;
   while (true) {
@@ -1031,19 +1036,22 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
       } else {
+        // one GPU: the pAp partials are summed by a passenger CTA of the gather-scatter launch
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
-        SEMB_TRY(reduce_partials(c, ax_num_partials(c, 0, c->E), 0, 1, &s->pAp, done));
-        SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(launch_gs(c, Ap, done, c->partials, ax_num_partials(c, 0, c->E), &s->pAp));
       }
       // x, r, rdotr                             (elliptic.py:56-60)
       {
         ProfScope ps(c, SEMB_K_UPDATE);
         c->launch_count++;
-        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, s, n, c->partials);
-        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, nullptr, s, n, c->partials);
+        // one GPU: the CTA that finishes last sums the partials and does the scalar step (ticket)
+        double* upart = c->partials;
+        unsigned int* ticket = multi ? nullptr : c->ticket;
+        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, s, n, upart, ticket, hist);
+        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, nullptr, s, n, upart, ticket, hist);
         SEMB_CUDA(cudaGetLastError());
       }
-      if (c->comm != nullptr && c->nranks > 1 && use_p2p(c)) {
+      if (multi && use_p2p(c)) {
         c->seq_scalar++;
         c->launch_count++;
         reduce_allreduce_kernel<true><<<1, RED_NT, 0, c->stream>>>(c->partials, grid, &s->rdotr_new, s, hist,
@@ -1054,9 +1062,6 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
         c->launch_count++;
         cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
-      } else {
-        c->launch_count++;
-        reduce_and_step_kernel<<<1, RED_NT, 0, c->stream>>>(c->partials, grid, s, hist);
       }
       SEMB_CUDA(cudaGetLastError());
       // p = z + beta p                          (elliptic.py:70)

@@ -75,13 +75,33 @@ struct GsPlan {
   int64_t n2, n4, n8;        // segments per class
   int64_t off2, off4, off8;  // start of each class in ids (multiples of 4 ints)
   int b2, b4, b8;            // blocks per class
+  // optional passenger: one more CTA (the last one) sums red_n per-CTA partials into *red_out while the
+  // gather-scatter runs -- in semb_cg this is the pAp reduction, which only the update kernel AFTER the
+  // gather-scatter needs, so it costs neither a launch nor time on the critical path
+  const double* red_src;
+  int64_t red_n;
+  double* red_out;
 };
+
+__device__ __forceinline__ double block_sum(double v);
 
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
                 const int* __restrict__ done) {
   if (done != nullptr && *done) return;
   int b = blockIdx.x;
+  if (b == plan.b2 + plan.b4 + plan.b8) {  // the passenger CTA (only launched when red_out is set)
+    double v0 = 0.0, v1 = 0.0;
+    int64_t t = threadIdx.x;
+    for (; t + VEC_NT < plan.red_n; t += 2 * VEC_NT) {
+      v0 += plan.red_src[t];
+      v1 += plan.red_src[t + VEC_NT];
+    }
+    for (; t < plan.red_n; t += VEC_NT) v0 += plan.red_src[t];
+    const double s = block_sum(v0 + v1);
+    if (threadIdx.x == 0) *plan.red_out = s;
+    return;
+  }
   if (b < plan.b2) {
     const int64_t stride = (int64_t)plan.b2 * VEC_NT;
     for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += 4 * stride)
@@ -380,6 +400,51 @@ __global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double t
   s->done = (early || !(0 < maxit && rdotr > s->TOL)) ? 1 : 0;
 }
 
+// After the update's reduction: beta, history, iteration count, stop test
+// (sempy/elliptic.py:47,59-71).
+__device__ __forceinline__ void cg_step_scalars(CgScalars* s, double* hist) {
+  const double r0 = s->rdotr, r1 = s->rdotr_new;
+  const double alpha = r0 / s->pAp;
+  const double beta = r1 / r0;
+  if (hist != nullptr) {
+    double* h = hist + 5 * (int64_t)s->niter;
+    h[0] = r0;
+    h[1] = r1;
+    h[2] = alpha;
+    h[3] = beta;
+    h[4] = s->pAp;
+  }
+  s->alpha = alpha;
+  s->beta = beta;
+  s->rdotr = r1;
+  s->niter += 1;
+  s->done = !(s->niter < s->maxit && r1 > s->TOL) ? 1 : 0;
+}
+
+// Single GPU: the CTA that finishes last adds the per-CTA partials (fixed order -> repeatable whichever
+// CTA it is) and performs the scalar step, so no separate reduction launch sits between the update and
+// the direction kernel.  ticket == nullptr (several GPUs) leaves that to reduce_allreduce_kernel.
+__device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* partials, unsigned int* ticket,
+                                                 double* hist) {
+  if (ticket == nullptr) return;
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();  // this CTA's partial is visible before its ticket
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (unsigned int t = threadIdx.x; t < gridDim.x; t += VEC_NT) v += __ldcg(partials + t);
+  const double tot = block_sum(v);
+  if (threadIdx.x == 0) {
+    s->rdotr_new = tot;
+    cg_step_scalars(s, hist);
+    *ticket = 0;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K3: x += alpha p ; r -= alpha Ap ; partial of sum rmult r r (or rmult r dinv r)
 // (sempy/elliptic.py:52-60; iterative.py:66-73).  56 B per node (+8 Jacobi).
@@ -392,7 +457,8 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                  const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
-                 const CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials) {
+                 CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                 double* __restrict__ hist) {
   if (s->done) return;
   __shared__ double s_rcp[256];
   s_rcp[threadIdx.x] = 1.0 / (double)(threadIdx.x > 0 ? threadIdx.x : 1);  // VEC_NT == 256 entries
@@ -436,60 +502,13 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   }
   const double sum = block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = sum;
+  cg_update_finish(s, partials, ticket, hist);
 }
 
-// After the update's reduction: beta, history, iteration count, stop test
-// (sempy/elliptic.py:47,59-71).
-__device__ __forceinline__ void cg_step_scalars(CgScalars* s, double* hist) {
-  const double r0 = s->rdotr, r1 = s->rdotr_new;
-  const double alpha = r0 / s->pAp;
-  const double beta = r1 / r0;
-  if (hist != nullptr) {
-    double* h = hist + 5 * (int64_t)s->niter;
-    h[0] = r0;
-    h[1] = r1;
-    h[2] = alpha;
-    h[3] = beta;
-    h[4] = s->pAp;
-  }
-  s->alpha = alpha;
-  s->beta = beta;
-  s->rdotr = r1;
-  s->niter += 1;
-  s->done = !(s->niter < s->maxit && r1 > s->TOL) ? 1 : 0;
-}
 __global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
   if (s->done) return;
   cg_step_scalars(s, hist);
 }
-// single GPU: reduction of the update's partials and the scalar step in one launch
-__global__ void __launch_bounds__(RED_NT)
-reduce_and_step_kernel(const double* __restrict__ partials, int64_t n, CgScalars* s, double* hist) {
-  if (s->done) return;
-  __shared__ double s_red[RED_NT / 32];
-  double v0 = 0.0, v1 = 0.0;
-  int64_t t = threadIdx.x;
-  for (; t + RED_NT < n; t += 2 * RED_NT) {
-    v0 += partials[t];
-    v1 += partials[t + RED_NT];
-  }
-  for (; t < n; t += RED_NT) v0 += partials[t];
-  double v = v0 + v1;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double w = s_red[threadIdx.x];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if (threadIdx.x == 0) {
-      s->rdotr_new = w;
-      cg_step_scalars(s, hist);
-    }
-  }
-}
-
 // Several GPUs: per-CTA partials -> rank sum -> all-rank sum (peer memory) in ONE launch, optionally
 // followed by the scalar step.  `done` is not consulted for the all-reduce itself: every rank must
 // take part in every exchange.
