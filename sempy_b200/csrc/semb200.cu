@@ -24,13 +24,6 @@ static int g_p2p_on = [] {  // 0: NCCL for the halo exchange and the scalar all-
   const char* v = getenv("SEMB_P2P");
   return v ? atoi(v) : 1;
 }();
-// L2 persistence for the operator output inside semb_cg (MB of L2 set aside; 0 = off).  Ap is written by
-// the operator kernel, read and rewritten by the gather-scatter and read by the update kernel: 32 B of
-// DRAM traffic per node and iteration for 8 B of data, the best ratio of all CG vectors.
-static int g_l2_persist_mb = [] {
-  const char* v = getenv("SEMB_L2_PERSIST_MB");
-  return v ? atoi(v) : 0;
-}();
 static int g_ax_tuned_high_order = [] {  // 0: plane-sweep kernel for every order but N = 7 (A/B)
   const char* v = getenv("SEMB_AX_TUNED_HIGH_ORDER");
   return v ? atoi(v) : 1;
@@ -991,27 +984,6 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
 
   const int* done = &s->done;
   const bool multi = c->comm != nullptr && c->nranks > 1;
-  // optional: keep (part of) Ap resident in the L2 set-aside for the duration of the solve
-  bool l2_window = false;
-  if (g_l2_persist_mb > 0) {
-    cudaDeviceProp prop;
-    SEMB_CUDA(cudaGetDeviceProperties(&prop, c->device));
-    const size_t want = (size_t)g_l2_persist_mb << 20;
-    const size_t carve = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
-    const size_t bytes = std::min<size_t>(sizeof(double) * (size_t)n, (size_t)prop.accessPolicyMaxWindowSize);
-    if (carve > 0 && bytes > 0) {
-      SEMB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-      cudaStreamAttrValue attr;
-      std::memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = Ap;
-      attr.accessPolicyWindow.num_bytes = bytes;
-      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      SEMB_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-      l2_window = true;
-    }
-  }
   int issued = 0;
   int chunk = 1;
   while (true) {
@@ -1103,13 +1075,6 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
     }
     issued += todo;
     chunk = std::min(chunk * 2, 16);
-  }
-  if (l2_window) {
-    cudaStreamAttrValue attr;
-    std::memset(&attr, 0, sizeof(attr));
-    attr.accessPolicyWindow.num_bytes = 0;
-    SEMB_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    SEMB_CUDA(cudaCtxResetPersistingL2Cache());
   }
   *niter = c->h_pinned[0];
   if (history != nullptr && *niter > 0)
@@ -1385,10 +1350,6 @@ int semb_set_tuning(const char* name, int value) {
   }
   if (std::strcmp(name, "ax_tuned_high_order") == 0) {
     g_ax_tuned_high_order = value;
-    return 0;
-  }
-  if (std::strcmp(name, "l2_persist_mb") == 0) {
-    g_l2_persist_mb = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {
