@@ -99,3 +99,17 @@ def test_halo_tables_reproduce_global_gather_scatter(size, dims, perturb, N, tmp
     expect_if = [plane * (1 if r in (0, size - 1) else 2) for r in range(size)]
     assert list(res[:, 4].astype(int)) == expect_if
     assert list(res[:, 5].astype(int)) == [1 if r in (0, size - 1) else 2 for r in range(size)]
+
+
+@pytest.mark.parametrize("size,dims,perturb,N", [(2, (3, 3, 3), 0.3, 3), (3, (2, 2, 5), 0.2, 2), (4, (3, 3, 3), 0.0, 2)])
+def test_non_planar_interfaces(size, dims, perturb, N, tmp_path):
+    """Element counts that do not divide into whole layers: the slab boundary cuts through a layer, so a
+    rank's interface is L-shaped and ranks can share nodes along edges and at corners only."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(size, _free_port(), dims, perturb, N, out), nprocs=size, join=True)
+    res = np.load(out)
+    assert res.shape[0] == size
+    assert res[:, 0].max() < 1e-15 and res[:, 1].all() and res[:, 2].all() and res[:, 3].all()
+    assert (res[:, 4] > 0).all()

@@ -173,6 +173,15 @@ def test_cg_edge_cases_and_verbose(capsys):
     x, it = elliptic_cg(m, g["b"], tol=1e-8, maxit=3, verbose=1)
     out = capsys.readouterr().out.splitlines()
     assert out[0].startswith("Initial rnorm=") and len(out) == 4 and out[1].startswith("niter=0 r0=") and " pap=" in out[3]
+    # the printed scalars (elliptic.py:63-68) are the reference's: r0, r1, alpha, beta, pAp per iteration
+    hist = []
+    geom = so_geom9(g)
+    so.elliptic_cg(lambda v: so.elliptic_ax(geom, v, int(g["N"]), g["D"]), g["mask"], g["global_to_local"],
+                   g["global_start"], g["rmult"], g["b"], tol=1e-8, maxit=3, history=hist)
+    for line, ref in zip(out[1:], hist):
+        vals = [float(tok.split("=")[1]) for tok in line.split()[1:]]
+        assert np.allclose(vals, ref, rtol=1e-11, atol=0)
+    assert abs(float(out[0].split("=")[1]) - hist[0][0]) <= 1e-12 * hist[0][0]
     xl, itl = elliptic_cg_loopy(m, g["b"], tol=1e-8, maxit=10000)
     assert itl == int(g["cg_niter_1e-08"]) or abs(itl - int(g["cg_niter_1e-08"])) <= 1
     b = g["b"].copy()
