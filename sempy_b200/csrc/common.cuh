@@ -73,15 +73,12 @@ const NcclApi& nccl();  // loads on first use; ok == false if no NCCL library co
 constexpr int kMaxNq = 16;
 constexpr int kNumSMs = 148;  // B200
 
-// D by value in the kernel parameter space (constant bank): after unrolling,
-// every D operand of a DFMA is a c[0][imm] operand and costs no register.
+// D by value in the kernel parameter space (constant bank): after unrolling, every D operand of a
+// DFMA is fetched with LDCU into a uniform register and costs no vector register.
 struct DMat {
   double d[kMaxNq * kMaxNq];  // row-major, leading dimension Nq
 };
-struct DMat8 {
-  double d[64];
-};
-// five private copies of D for the five phases of ax8_kernel (see line8)
+// five private copies of D for the five phases of ax8_kernel (see line8x2)
 struct DMat8x {
   double d[5][64];
 };

@@ -18,20 +18,18 @@ namespace semb {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
-// tuning knob for A/B measurements: bulk L2 prefetch of G in the Nq = 8 Ax kernel (default on);
-// SEMB_AX_L2_PREFETCH=0 or semb_set_tuning("ax_l2_prefetch", 0) turns it off
-static int g_p2p_on = [] {  // 0: NCCL for the halo exchange and the scalar all-reduces (A/B against the peer-memory path)
-  const char* v = getenv("SEMB_P2P");
-  return v ? atoi(v) : 1;
-}();
-static int g_ax_tuned_high_order = [] {  // 0: plane-sweep kernel for every order but N = 7 (A/B)
-  const char* v = getenv("SEMB_AX_TUNED_HIGH_ORDER");
-  return v ? atoi(v) : 1;
-}();
-static int g_ax_l2_prefetch = [] {
-  const char* v = getenv("SEMB_AX_L2_PREFETCH");
-  return v ? atoi(v) : 1;
-}();
+// Tuning knobs for A/B measurements (environment at load time, or semb_set_tuning at run time).
+// None of them changes results.
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : fallback;
+}
+// "p2p": 0 = NCCL for the halo exchange and the scalar all-reduces instead of the peer-memory path
+static int g_p2p_on = env_int("SEMB_P2P", 1);
+// "ax_tuned_high_order": 0 = plane-sweep kernel for every order but N = 7
+static int g_ax_tuned_high_order = env_int("SEMB_AX_TUNED_HIGH_ORDER", 1);
+// "ax_l2_prefetch": 0 = no bulk L2 prefetch of G in the tuned Ax kernels
+static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
 
 const NcclApi& nccl() {
   static NcclApi api = [] {
@@ -415,6 +413,9 @@ static int upload(T** dst, const T* src, size_t count) {
   *dst = nullptr;
   SEMB_CUDA(cudaMalloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
   if (count) SEMB_CUDA(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+  // a pageable-memory cudaMemcpy may return before its DMA has landed, and the context's stream is
+  // non-blocking (no implicit ordering with the default stream): make the table resident here
+  SEMB_CUDA(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -456,6 +457,7 @@ int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq) {
   SEMB_CUDA(cudaMalloc(&c->ticket, 4 * sizeof(unsigned int)));
   SEMB_CUDA(cudaMemset(c->ticket, 0, 4 * sizeof(unsigned int)));
   if (ensure_partials(c)) return 1;
+  SEMB_CUDA(cudaDeviceSynchronize());  // the memsets above ran on the default stream
   *out = c;
   return 0;
 }
@@ -623,6 +625,7 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   SEMB_CUDA(cudaMemcpy(c->gs_ids, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
   SEMB_CUDA(cudaMalloc(&c->gs_var_start, sizeof(int32_t) * var_start.size()));
   SEMB_CUDA(cudaMemcpy(c->gs_var_start, var_start.data(), sizeof(int32_t) * var_start.size(), cudaMemcpyHostToDevice));
+  SEMB_CUDA(cudaDeviceSynchronize());  // uploads done before the context's (non-blocking) stream uses them
   c->have_gs = true;
   return build_rmult(c);
 }
@@ -645,6 +648,7 @@ int semb_set_mask(semb_ctx* c, const int64_t* mask_ids, int64_t n_mask) {
   SEMB_CUDA(cudaMemcpy(c->maskbits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
   SEMB_CUDA(cudaMalloc(&c->mask_ids, sizeof(int64_t) * std::max<int64_t>(n_mask, 1)));
   if (n_mask) SEMB_CUDA(cudaMemcpy(c->mask_ids, mask_ids, sizeof(int64_t) * n_mask, cudaMemcpyHostToDevice));
+  SEMB_CUDA(cudaDeviceSynchronize());
   c->n_mask = n_mask;
   c->have_mask = true;
   if (c->vec[4]) {
