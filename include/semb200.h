@@ -197,9 +197,7 @@ int64_t semb_launch_count(semb_ctx* ctx);
 /* Process-wide tuning knobs for A/B measurements; results do not depend on
  * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
  * factors in the N = 7 Ax kernel.  "p2p": 1 (default) / 0, peer-memory transport
- * vs NCCL for the halo exchange and the scalar all-reduces.  "gs_chunks": n > 1 makes
- * semb_cg (one GPU) pipeline operator and gather-scatter over n element chunks on two
- * streams; read by semb_set_gather_scatter; default 1. */
+ * vs NCCL for the halo exchange and the scalar all-reduces. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

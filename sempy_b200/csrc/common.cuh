@@ -148,15 +148,6 @@ struct semb_ctx {
   int64_t gs_var_nseg = 0;
   int64_t gs_var_off = 0;
   bool have_gs = false;
-  // optional chunking of the schedule (tuning knob "gs_chunks" at schedule-build time): segments are
-  // grouped by the element chunk that completes them, so that semb_cg can run the gather-scatter of
-  // chunk c (second stream) while the operator kernel works on chunk c+1 and the output is still in L2
-  int gs_chunks = 1;
-  std::vector<int64_t> chunk_e;    // element bounds of the chunks (gs_chunks + 1)
-  std::vector<int64_t> chunk_cnt;  // segments per (chunk, class): [chunk * 3 + class]
-  cudaStream_t aux_stream = nullptr;
-  std::vector<cudaEvent_t> chunk_ev;
-  cudaEvent_t ev_join = nullptr;
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 

@@ -28,9 +28,6 @@ static int env_int(const char* name, int fallback) {
 static int g_p2p_on = env_int("SEMB_P2P", 1);
 // "ax_tuned_high_order": 0 = plane-sweep kernel for every order but N = 7
 static int g_ax_tuned_high_order = env_int("SEMB_AX_TUNED_HIGH_ORDER", 1);
-// "gs_chunks": > 1 = semb_cg pipelines the operator and the gather-scatter over that many element
-// chunks on two streams (read when the gather-scatter schedule is built; 1 = one pass, the default)
-static int g_gs_chunks = env_int("SEMB_GS_CHUNKS", 1);
 // "ax_l2_prefetch": 0 = no bulk L2 prefetch of G in the tuned Ax kernels
 static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
 
@@ -212,14 +209,19 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 }
 
 // ---- K2 dispatch -----------------------------------------------------------
-// fixed-length classes: n segments starting at ids offset off, per class (2, 4, 8); optional passenger
-static int launch_gs_plan(semb_ctx* c, double* x, const int64_t (&nseg)[3], const int64_t (&off)[3], cudaStream_t st,
-                          const int* done, const double* red_src, int64_t red_n, double* red_out) {
-  GsPlan plan{nseg[0], nseg[1], nseg[2], off[0], off[1], off[2], 0, 0, 0, red_src, red_n, red_out};
+static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_src = nullptr, int64_t red_n = 0,
+                     double* red_out = nullptr) {
+  ProfScope ps(c, SEMB_K_GS);
+  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0, red_src, red_n, red_out};
+  for (const GsClass& k : c->gs_classes) {
+    if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
+    else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
+    else if (k.len == 8) { plan.n8 = k.nseg; plan.off8 = k.off; }
+  }
   // blocks per class in proportion to their loads+stores; each thread takes 4 / 2 / 1 segments per trip
-  auto blocks_for = [](int64_t n, int per_thread) {
-    if (n == 0) return 0;
-    const int64_t want = (n + (int64_t)VEC_NT * per_thread - 1) / ((int64_t)VEC_NT * per_thread);
+  auto blocks_for = [](int64_t nseg, int per_thread) {
+    if (nseg == 0) return 0;
+    const int64_t want = (nseg + (int64_t)VEC_NT * per_thread - 1) / ((int64_t)VEC_NT * per_thread);
     return (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8);
   };
   plan.b2 = blocks_for(plan.n2, 4);
@@ -228,12 +230,9 @@ static int launch_gs_plan(semb_ctx* c, double* x, const int64_t (&nseg)[3], cons
   const int total_blocks = plan.b2 + plan.b4 + plan.b8 + (red_out != nullptr ? 1 : 0);
   if (total_blocks > 0) {
     c->launch_count++;
-    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, st>>>(x, c->gs_ids, plan, done);
+    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
     SEMB_CUDA(cudaGetLastError());
   }
-  return 0;
-}
-static int launch_gs_var(semb_ctx* c, double* x, const int* done) {
   if (c->gs_var_nseg > 0) {
     c->launch_count++;
     gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
@@ -241,19 +240,6 @@ static int launch_gs_var(semb_ctx* c, double* x, const int* done) {
     SEMB_CUDA(cudaGetLastError());
   }
   return 0;
-}
-// the whole local gather-scatter in one pass on the context's stream
-static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_src = nullptr, int64_t red_n = 0,
-                     double* red_out = nullptr) {
-  ProfScope ps(c, SEMB_K_GS);
-  int64_t nseg[3] = {0, 0, 0}, off[3] = {0, 0, 0};
-  for (const GsClass& k : c->gs_classes) {
-    const int q = k.len == 2 ? 0 : k.len == 4 ? 1 : 2;
-    nseg[q] = k.nseg;
-    off[q] = k.off;
-  }
-  SEMB_TRY(launch_gs_plan(c, x, nseg, off, c->stream, done, red_src, red_n, red_out));
-  return launch_gs_var(c, x, done);
 }
 
 // ---- multi-GPU halo --------------------------------------------------------
@@ -408,17 +394,6 @@ static int build_rmult(semb_ctx* c) {
   return 0;
 }
 
-static int ensure_chunk_streams(semb_ctx* c) {
-  if (c->aux_stream == nullptr) SEMB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-  if (c->ev_join == nullptr) SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  while ((int)c->chunk_ev.size() < c->gs_chunks) {
-    cudaEvent_t ev;
-    SEMB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    c->chunk_ev.push_back(ev);
-  }
-  return 0;
-}
-
 static int build_jacobi(semb_ctx* c) {
   SEMB_TRY(ensure_vec(c, 4));
   double* d = c->vec[4];
@@ -522,9 +497,6 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->ll_error);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
-  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
-  for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
   if (c->ev_if_done) cudaEventDestroy(c->ev_if_done);
   if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
   if (c->ev_exchanged) cudaEventDestroy(c->ev_exchanged);
@@ -604,42 +576,22 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
              "semb_set_gather_scatter: global_start must run from 0 to E*Np");
   SEMB_TRY(bind_device(c));
   // Classify the segments with more than one local copy by length.
-  struct Seg {
-    int32_t chunk, first;
-    int64_t seg;
-  };
-  std::vector<Seg> cls[4];  // len 2, 4, 8, other
-  const int nch = (g_gs_chunks > 1 && c->E >= 2 * (int64_t)g_gs_chunks) ? g_gs_chunks : 1;
-  const int64_t chunkE = (c->E + nch - 1) / nch;
+  std::vector<std::pair<int32_t, int64_t>> cls[4];  // len 2, 4, 8, other : (first local id, segment)
   for (int64_t s = 0; s < nglobal; ++s) {
     const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
     SEMB_CHECK(len >= 1, "semb_set_gather_scatter: empty segment");
     if (len == 1) continue;
-    int64_t first = g2l[lo], last = g2l[lo];
-    for (int64_t q = lo + 1; q < lo + len; ++q) {
-      first = std::min(first, g2l[q]);
-      last = std::max(last, g2l[q]);
-    }
-    SEMB_CHECK(first >= 0 && last < c->n, "semb_set_gather_scatter: local index out of range");
+    int64_t first = g2l[lo];
+    for (int64_t q = lo + 1; q < lo + len; ++q) first = std::min(first, g2l[q]);
+    SEMB_CHECK(first >= 0 && first < c->n, "semb_set_gather_scatter: local index out of range");
     const int k = len == 2 ? 0 : len == 4 ? 1 : len == 8 ? 2 : 3;
-    // the chunk whose operator output completes the segment = the chunk of its last copy
-    const int32_t chunk = nch > 1 ? (int32_t)std::min<int64_t>(nch - 1, (last / c->Np) / chunkE) : 0;
-    cls[k].push_back(Seg{chunk, (int32_t)first, s});
+    cls[k].emplace_back((int32_t)first, s);
   }
-  // Order segments by their first local index so that neighbouring threads touch neighbouring memory.
-  // One pass (nch == 1): DESCENDING -- the operator kernel before the gather-scatter writes its output in
-  // ascending element order, so its tail is what may still be in L2.  Chunked: by chunk, then ascending.
-  for (auto& v : cls)
-    std::sort(v.begin(), v.end(), [nch](const Seg& a, const Seg& b) {
-      if (nch > 1) return a.chunk != b.chunk ? a.chunk < b.chunk : a.first < b.first;
-      return a.first > b.first;
-    });
-  c->gs_chunks = nch;
-  c->chunk_e.assign(nch + 1, 0);
-  for (int q = 0; q <= nch; ++q) c->chunk_e[q] = std::min<int64_t>(c->E, q * chunkE);
-  c->chunk_cnt.assign((size_t)nch * 3, 0);
-  for (int k = 0; k < 3; ++k)
-    for (const Seg& sg : cls[k]) c->chunk_cnt[(size_t)sg.chunk * 3 + k]++;
+  // Order segments by their first local index so that neighbouring threads touch neighbouring
+  // memory -- DESCENDING: the operator kernel before the gather-scatter writes its output in ascending
+  // element order, so its tail is what is still in L2; walking backwards reads that first, and leaves
+  // the head of the vector in L2 for the ascending update kernel that follows.
+  for (auto& v : cls) std::sort(v.begin(), v.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& b) { return a > b; });
   std::vector<int32_t> ids;
   std::vector<int32_t> var_start;
   c->gs_classes.clear();
@@ -653,15 +605,15 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   for (int k = 0; k < 3; ++k) {
     while (ids.size() % 4) ids.push_back(0);
     GsClass gc{lens[k], (int64_t)cls[k].size(), (int64_t)ids.size()};
-    for (auto& sg : cls[k]) emit(sg.seg);
+    for (auto& pr : cls[k]) emit(pr.second);
     c->gs_classes.push_back(gc);
   }
   while (ids.size() % 4) ids.push_back(0);
   c->gs_var_off = (int64_t)ids.size();
   c->gs_var_nseg = (int64_t)cls[3].size();
   var_start.push_back(0);
-  for (auto& sg : cls[3]) {
-    emit(sg.seg);
+  for (auto& pr : cls[3]) {
+    emit(pr.second);
     var_start.push_back((int32_t)(ids.size() - c->gs_var_off));
   }
   c->gs_nids = (int64_t)ids.size();
@@ -1087,29 +1039,6 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(launch_gs(c, Ap, done));
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
-      } else if (c->gs_chunks > 1) {
-        // one GPU, chunked: operator on chunk q (main stream), gather-scatter of the segments completed by
-        // chunk q on the second stream while the operator continues with chunk q+1
-        SEMB_TRY(ensure_chunk_streams(c));
-        int64_t np = 0, off[3] = {0, 0, 0};
-        for (const GsClass& k : c->gs_classes) off[k.len == 2 ? 0 : k.len == 4 ? 1 : 2] = k.off;
-        for (int q = 0; q < c->gs_chunks; ++q) {
-          const int64_t e0 = c->chunk_e[q], e1 = c->chunk_e[q + 1];
-          SEMB_TRY(launch_ax(c, p, Ap, mask, true, e0, e1, done, np));
-          np += ax_num_partials(c, e0, e1);
-          SEMB_CUDA(cudaEventRecord(c->chunk_ev[q], c->stream));
-          SEMB_CUDA(cudaStreamWaitEvent(c->aux_stream, c->chunk_ev[q], 0));
-          const int64_t nseg[3] = {c->chunk_cnt[(size_t)q * 3], c->chunk_cnt[(size_t)q * 3 + 1], c->chunk_cnt[(size_t)q * 3 + 2]};
-          const bool last = q == c->gs_chunks - 1;
-          SEMB_TRY(launch_gs_plan(c, Ap, nseg, off, c->aux_stream, done, last ? c->partials : nullptr, last ? np : 0,
-                                  last ? &s->pAp : nullptr));
-          off[0] += 2 * nseg[0];
-          off[1] += 4 * nseg[1];
-          off[2] += 8 * nseg[2];
-        }
-        SEMB_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
-        SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-        SEMB_TRY(launch_gs_var(c, Ap, done));
       } else {
         // one GPU: the pAp partials are summed by a passenger CTA of the gather-scatter launch
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
@@ -1425,10 +1354,6 @@ int semb_set_tuning(const char* name, int value) {
   }
   if (std::strcmp(name, "ax_tuned_high_order") == 0) {
     g_ax_tuned_high_order = value;
-    return 0;
-  }
-  if (std::strcmp(name, "gs_chunks") == 0) {
-    g_gs_chunks = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {
