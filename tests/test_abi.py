@@ -46,3 +46,28 @@ def test_no_cpu_fallback_in_product():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("no CPU fallback", ""), fn
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every prototype in semb200.h has as many parameters as its ctypes entry (a mismatch would corrupt
+    the call stack only at run time, on the GPU box)."""
+    hdr = open(os.path.join(ROOT, "include", "semb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(semb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    seen = 0
+    for name, params in protos:
+        if name == "semb_apply_fn":
+            continue
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert name in _capi.SIGNATURES, name
+        assert len(_capi.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes table {len(_capi.SIGNATURES[name][1])}"
+        seen += 1
+    assert seen == len(_capi.SIGNATURES)
+
+
+def test_build_targets_sm_100a():
+    sh = open(os.path.join(ROOT, "sempy_b200", "csrc", "build.sh")).read()
+    assert "arch=compute_100a,code=sm_100a" in sh and "-lineinfo" in sh
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert "build.sh" in entry
