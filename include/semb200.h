@@ -178,6 +178,16 @@ int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* 
 int semb_p2p_alloc(semb_ctx* ctx, int64_t halo_capacity, char* handle64);
 int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv_off);
 
+/* Host-only helper (no device needed): the closure tables of the experimental fused operator +
+ * gather-scatter kernel (tuning knob "ax_fused_gs", off by default), exposed so that the schedule can be
+ * unit-tested on a CPU.  Segments are grouped by the element that holds their highest local index.
+ * First call with base == NULL: sizes[0] = len(ids), sizes[1] = len(dep_elem), sizes[2] = number of
+ * segments whose length is not 2, 4 or 8.  Second call fills base, dep_start (int32[E+1]), n2, n4, n8
+ * (uint16[E]), ids and dep_elem. */
+int semb_host_closure_tables(int64_t E, int64_t Np, const int64_t* g2l, const int64_t* gstart, int64_t nglobal,
+                             int64_t* sizes, int32_t* base, uint16_t* n2, uint16_t* n4, uint16_t* n8, int32_t* ids,
+                             int32_t* dep_start, int32_t* dep_elem);
+
 /* ---- device memory helpers for callers without their own allocator ------ */
 int semb_malloc(int device, void** ptr, int64_t bytes);
 int semb_free(int device, void* ptr);
@@ -197,7 +207,8 @@ int64_t semb_launch_count(semb_ctx* ctx);
 /* Process-wide tuning knobs for A/B measurements; results do not depend on
  * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
  * factors in the N = 7 Ax kernel.  "p2p": 1 (default) / 0, peer-memory transport
- * vs NCCL for the halo exchange and the scalar all-reduces. */
+ * vs NCCL for the halo exchange and the scalar all-reduces.  "ax_fused_gs" (0) / "ax_fused_lag":
+ * EXPERIMENTAL persistent operator + gather-scatter kernel inside semb_cg, not yet measured. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

@@ -78,6 +78,11 @@ SIGNATURES = {
     ),
     "semb_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
     "semb_p2p_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    "semb_host_closure_tables": (
+        C.c_int,
+        [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
     "semb_free": (C.c_int, [C.c_int, C.c_void_p]),
     "semb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),

@@ -148,6 +148,13 @@ struct semb_ctx {
   int64_t gs_var_nseg = 0;
   int64_t gs_var_off = 0;
   bool have_gs = false;
+  // experimental fused operator + gather-scatter (ax8_fused.cuh): closure tables, work counters, flags
+  bool fused_ready = false;
+  int32_t *fz_base = nullptr, *fz_ids = nullptr, *fz_dep_start = nullptr, *fz_dep_elem = nullptr;
+  uint16_t *fz_n2 = nullptr, *fz_n4 = nullptr, *fz_n8 = nullptr;
+  unsigned int *fz_work = nullptr, *fz_flag = nullptr;
+  int* fz_err = nullptr;
+  unsigned int fz_tag = 0;
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 

@@ -7,8 +7,10 @@
 #include <numeric>
 #include <utility>
 
+#include "ax8_fused.cuh"
 #include "ax_kernels.cuh"
 #include "axl_kernels.cuh"
+#include "closure_tables.h"
 #include "common.cuh"
 #include "setup_kernels.cuh"
 #include "vec_kernels.cuh"
@@ -28,6 +30,10 @@ static int env_int(const char* name, int fallback) {
 static int g_p2p_on = env_int("SEMB_P2P", 1);
 // "ax_tuned_high_order": 0 = plane-sweep kernel for every order but N = 7
 static int g_ax_tuned_high_order = env_int("SEMB_AX_TUNED_HIGH_ORDER", 1);
+// "ax_fused_gs": 1 = EXPERIMENTAL persistent operator + gather-scatter kernel inside semb_cg (N = 7, one
+// GPU; ax8_fused.cuh); read when the gather-scatter schedule is built.  "ax_fused_lag": its closing lag.
+static int g_ax_fused_gs = env_int("SEMB_AX_FUSED_GS", 0);
+static int g_ax_fused_lag = env_int("SEMB_AX_FUSED_LAG", 2368);
 // "ax_l2_prefetch": 0 = no bulk L2 prefetch of G in the tuned Ax kernels
 static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
 
@@ -233,6 +239,37 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_
     gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
     SEMB_CUDA(cudaGetLastError());
   }
+  if (c->gs_var_nseg > 0) {
+    c->launch_count++;
+    gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
+                                                                      c->gs_var_nseg, done);
+    SEMB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// EXPERIMENTAL fused operator + gather-scatter (see ax8_fused.cuh); mask + dot variant only
+static int launch_ax_fused(semb_ctx* c, const double* p, double* ap, double* dot_out, const int* done) {
+  ProfScope ps(c, SEMB_K_AX);
+  static bool attr_done[64] = {false};
+  if (!attr_done[c->device & 63]) {
+    SEMB_CUDA(cudaFuncSetAttribute(ax8_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX8_SMEM));
+    SEMB_CUDA(cudaFuncSetAttribute(ax8_fused_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done[c->device & 63] = true;
+  }
+  DMat8x d8;
+  for (int q = 0; q < 5; ++q) std::memcpy(d8.d[q], c->D.d, sizeof(d8.d[q]));
+  FusedGsTables gt{c->fz_base, c->fz_n2, c->fz_n4, c->fz_n8, c->fz_ids, c->fz_dep_start, c->fz_dep_elem};
+  const int lag = std::max(1, g_ax_fused_lag);
+  c->fz_tag++;
+  c->launch_count++;
+  ax8_fused_kernel<true, true><<<kNumSMs * 4, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(
+      p, c->G6, ap, reinterpret_cast<const unsigned long long*>(c->maskbits), c->partials, dot_out, (int)c->E, d8, done, gt,
+      c->fz_work, c->fz_flag, c->fz_tag, lag, c->fz_err);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+static int launch_gs_var_only(semb_ctx* c, double* x, const int* done) {
   if (c->gs_var_nseg > 0) {
     c->launch_count++;
     gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
@@ -476,6 +513,16 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->partials);
   cudaFree(c->scal);
   cudaFree(c->ticket);
+  cudaFree(c->fz_base);
+  cudaFree(c->fz_n2);
+  cudaFree(c->fz_n4);
+  cudaFree(c->fz_n8);
+  cudaFree(c->fz_ids);
+  cudaFree(c->fz_dep_start);
+  cudaFree(c->fz_dep_elem);
+  cudaFree(c->fz_work);
+  cudaFree(c->fz_flag);
+  cudaFree(c->fz_err);
   cudaFree(c->hist);
   for (double* v : c->vec) cudaFree(v);
   cudaFreeHost(c->h_pinned);
@@ -627,6 +674,29 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   SEMB_CUDA(cudaMemcpy(c->gs_var_start, var_start.data(), sizeof(int32_t) * var_start.size(), cudaMemcpyHostToDevice));
   SEMB_CUDA(cudaDeviceSynchronize());  // uploads done before the context's (non-blocking) stream uses them
   c->have_gs = true;
+  c->fused_ready = false;
+  if (g_ax_fused_gs && c->Nq == 8) {
+    ClosureTables t;
+    SEMB_CHECK(build_closure_tables(c->E, c->Np, g2l, gstart, nglobal, t) == 0, "semb_set_gather_scatter: closure tables failed");
+    SEMB_TRY(upload(&c->fz_base, t.base.data(), t.base.size()));
+    SEMB_TRY(upload(&c->fz_n2, t.n2.data(), t.n2.size()));
+    SEMB_TRY(upload(&c->fz_n4, t.n4.data(), t.n4.size()));
+    SEMB_TRY(upload(&c->fz_n8, t.n8.data(), t.n8.size()));
+    SEMB_TRY(upload(&c->fz_ids, t.ids.data(), t.ids.size()));
+    SEMB_TRY(upload(&c->fz_dep_start, t.dep_start.data(), t.dep_start.size()));
+    SEMB_TRY(upload(&c->fz_dep_elem, t.dep_elem.data(), t.dep_elem.size()));
+    if (!c->fz_work) {
+      SEMB_CUDA(cudaMalloc(&c->fz_work, 4 * sizeof(unsigned int)));
+      SEMB_CUDA(cudaMalloc(&c->fz_flag, sizeof(unsigned int) * (size_t)c->E));
+      SEMB_CUDA(cudaMalloc(&c->fz_err, sizeof(int)));
+    }
+    SEMB_CUDA(cudaMemset(c->fz_work, 0, 4 * sizeof(unsigned int)));
+    SEMB_CUDA(cudaMemset(c->fz_flag, 0, sizeof(unsigned int) * (size_t)c->E));
+    SEMB_CUDA(cudaMemset(c->fz_err, 0, sizeof(int)));
+    SEMB_CUDA(cudaDeviceSynchronize());
+    c->fz_tag = 0;
+    c->fused_ready = true;
+  }
   return build_rmult(c);
 }
 
@@ -995,10 +1065,17 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
     c->h_pinned[2] = 0;
     if (c->p2p && c->ll_error)
       SEMB_CUDA(cudaMemcpyAsync(c->h_pinned + 2, c->ll_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    c->h_pinned[3] = 0;
+    if (c->fused_ready && g_ax_fused_gs)
+      SEMB_CUDA(cudaMemcpyAsync(c->h_pinned + 3, c->fz_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SEMB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->h_pinned[2]) {
       set_error("peer-memory exchange timed out: a neighbouring rank did not deliver (rank failure or table mismatch)");
       return 4;
+    }
+    if (c->h_pinned[3]) {
+      set_error("fused operator/gather-scatter kernel: a dependency wait timed out (experimental path, ax_fused_gs)");
+      return 5;
     }
     if (c->h_pinned[1] || issued >= maxit) break;
     const int todo = std::min(chunk, maxit - issued);
@@ -1039,6 +1116,10 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(launch_gs(c, Ap, done));
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
+      } else if (c->fused_ready && g_ax_fused_gs && mask) {
+        // EXPERIMENTAL: one persistent kernel computes Ap, the local pAp and the gather-scatter
+        SEMB_TRY(launch_ax_fused(c, p, Ap, &s->pAp, done));
+        SEMB_TRY(launch_gs_var_only(c, Ap, done));
       } else {
         // one GPU: the pAp partials are summed by a passenger CTA of the gather-scatter launch
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
@@ -1285,6 +1366,30 @@ int semb_p2p_attach(semb_ctx* c, const char* handles, const int64_t* peer_recv_o
   return 0;
 }
 
+// Host-only: closure tables of the experimental fused kernel, for unit tests (no device needed).
+// Call with out pointers NULL to get the sizes: sizes[0] = len(ids), sizes[1] = len(dep_elem), sizes[2] =
+// segments of other lengths.  Arrays: base, dep_start int32[E+1]; n2, n4, n8 uint16[E].
+int semb_host_closure_tables(int64_t E, int64_t Np, const int64_t* g2l, const int64_t* gstart, int64_t nglobal,
+                             int64_t* sizes, int32_t* base, uint16_t* n2, uint16_t* n4, uint16_t* n8, int32_t* ids,
+                             int32_t* dep_start, int32_t* dep_elem) {
+  SEMB_CHECK(sizes != nullptr, "semb_host_closure_tables: sizes is NULL");
+  ClosureTables t;
+  const int rc = build_closure_tables(E, Np, g2l, gstart, nglobal, t);
+  SEMB_CHECK(rc == 0, "semb_host_closure_tables: bad input or too many segments per element");
+  sizes[0] = (int64_t)t.ids.size();
+  sizes[1] = (int64_t)t.dep_elem.size();
+  sizes[2] = t.other_segments;
+  if (base == nullptr) return 0;
+  std::memcpy(base, t.base.data(), sizeof(int32_t) * t.base.size());
+  std::memcpy(dep_start, t.dep_start.data(), sizeof(int32_t) * t.dep_start.size());
+  std::memcpy(n2, t.n2.data(), sizeof(uint16_t) * t.n2.size());
+  std::memcpy(n4, t.n4.data(), sizeof(uint16_t) * t.n4.size());
+  std::memcpy(n8, t.n8.data(), sizeof(uint16_t) * t.n8.size());
+  if (!t.ids.empty()) std::memcpy(ids, t.ids.data(), sizeof(int32_t) * t.ids.size());
+  if (!t.dep_elem.empty()) std::memcpy(dep_elem, t.dep_elem.data(), sizeof(int32_t) * t.dep_elem.size());
+  return 0;
+}
+
 // ---- memory helpers --------------------------------------------------------
 int semb_malloc(int device, void** ptr, int64_t bytes) {
   SEMB_CHECK(ptr && bytes >= 0, "semb_malloc: bad argument");
@@ -1354,6 +1459,14 @@ int semb_set_tuning(const char* name, int value) {
   }
   if (std::strcmp(name, "ax_tuned_high_order") == 0) {
     g_ax_tuned_high_order = value;
+    return 0;
+  }
+  if (std::strcmp(name, "ax_fused_gs") == 0) {
+    g_ax_fused_gs = value;
+    return 0;
+  }
+  if (std::strcmp(name, "ax_fused_lag") == 0) {
+    g_ax_fused_lag = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {
