@@ -187,6 +187,20 @@ def build_halo(comm, xe, ye, ze, cand, global_id, g2l, gstart, numbering):
                 copy_start=copy_start.astype(np.int64), copy_ids=copy_ids.astype(np.int32))
 
 
+def peer_receive_offsets(layouts, me, nb_rank):
+    """Where this rank's block starts in each neighbour's receive layout (argument of semb_p2p_attach).
+
+    layouts[q] = (neighbour ranks of q, entry counts of q) as q passed them to semb_set_halo; a rank's
+    receive region mirrors its send region, block by block in that order, so my block for q starts after
+    the blocks of q's neighbours listed before me."""
+    out = []
+    for q in nb_rank:
+        ranks_q, counts_q = layouts[int(q)]
+        at = list(ranks_q).index(me)
+        out.append(int(sum(counts_q[:at])))
+    return np.ascontiguousarray(out, dtype=np.int64)
+
+
 def emulate_gather_scatter(comm, halo, x, g2l, gstart):
     """NumPy statement of what the device does with the tables (used by the CPU
     tests of this module and as executable documentation): returns dssum(x)."""

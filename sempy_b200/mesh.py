@@ -431,13 +431,7 @@ class Mesh:
             _capi.check(lib.semb_p2p_alloc(ctx.handle, cap, handle))
             everyone = self.comm.allgather((bytes(handle.raw), [int(q) for q in h["nb_rank"]],
                                             [int(n) for n in h["nb_count"]]))
-            me = self.comm.rank
-            peer_off = []
-            for q in h["nb_rank"]:
-                _hq, ranks_q, counts_q = everyone[int(q)]
-                at = ranks_q.index(me)
-                peer_off.append(sum(counts_q[:at]))
-            peer_off = np.ascontiguousarray(peer_off, dtype=np.int64)
+            peer_off = distributed.peer_receive_offsets([(e[1], e[2]) for e in everyone], self.comm.rank, h["nb_rank"])
             blob = b"".join(e[0] for e in everyone)
             _capi.check(lib.semb_p2p_attach(ctx.handle, blob, peer_off.ctypes.data))
             ctx.p2p_ready = True

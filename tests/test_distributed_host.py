@@ -36,6 +36,16 @@ def test_candidates_cover_the_interface_nodes():
     assert n_if == 6 and sorted(order[:6]) == list(range(6, 12))
 
 
+def test_peer_receive_offsets():
+    # four slabs: 0 | 1 | 2 | 3 with interface sizes 10, 20, 30
+    layouts = [([1], [10]), ([0, 2], [10, 20]), ([1, 3], [20, 30]), ([2], [30])]
+    assert list(dd.peer_receive_offsets(layouts, 0, [1])) == [0]        # rank 1 receives rank 0's block first
+    assert list(dd.peer_receive_offsets(layouts, 1, [0, 2])) == [0, 0]
+    assert list(dd.peer_receive_offsets(layouts, 2, [1, 3])) == [10, 0]  # after rank 0's 10 entries at rank 1
+    assert list(dd.peer_receive_offsets(layouts, 3, [2])) == [20]
+    assert dd.peer_receive_offsets(layouts, 3, [2]).dtype == np.int64
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
