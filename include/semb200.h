@@ -36,9 +36,11 @@ enum { SEMB_G9 = 9 /* (E,3,3,Np), mesh.get_geom() */, SEMB_G6 = 6 /* (E,6,Np): r
 /* flags of semb_ax */
 enum { SEMB_AX_MASK = 1 /* zero Dirichlet nodes */, SEMB_AX_GS = 2 /* then gather-scatter */ };
 /* preconditioner of semb_cg */
-enum { SEMB_PRECOND_NONE = 0, SEMB_PRECOND_JACOBI = 1 };
+enum { SEMB_PRECOND_NONE = 0, SEMB_PRECOND_JACOBI = 1, SEMB_PRECOND_FDM = 2 };
 /* kernels that can be timed with semb_profile_* */
-enum { SEMB_K_AX = 0, SEMB_K_GS = 1, SEMB_K_UPDATE = 2, SEMB_K_DIRECTION = 3, SEMB_K_COUNT = 4 };
+enum { SEMB_K_AX = 0 /* fused operator (+ direction update, mask, pAp) */, SEMB_K_GS = 1 /* gather-scatter pass */,
+       SEMB_K_UPDATE = 2 /* CG update (+ pulled gather-scatter, r.z, scalar step) */,
+       SEMB_K_DIRECTION = 3 /* preconditioner application (FDM) */, SEMB_K_COUNT = 4 };
 
 int semb_version(void);
 /* Text of the last error on the calling thread ("" if none). */
@@ -66,12 +68,35 @@ int semb_set_derivative(semb_ctx* ctx, const double* D);
 int semb_set_geom(semb_ctx* ctx, const double* G, int layout, int mem);
 /* Gather-scatter tables = Mesh.get_global_to_local_map() (sempy/mesh.py:422-423,
  * 479-480): local indices sorted by global id and the nglobal+1 segment
- * offsets.  Replaces gslib's GS.setup (mesh.py:437-438).  Also builds
- * rmult = 1/multiplicity (mesh.py:440-442). */
+ * offsets (HOST or DEVICE arrays, `mem`).  Replaces gslib's GS.setup
+ * (mesh.py:437-438); the schedule (segments with more than one copy, grouped by
+ * length, copies in ascending local index, plus the per-node links of the pull
+ * form) is built on the device.  Also builds rmult = 1/multiplicity
+ * (mesh.py:440-442). */
 int semb_set_gather_scatter(semb_ctx* ctx, const int64_t* global_to_local, const int64_t* global_start,
-                            int64_t nglobal);
-/* Dirichlet nodes = Mesh.get_mask_ids() (sempy/mesh.py:482-485). */
+                            int64_t nglobal, int mem);
+/* Dirichlet nodes = Mesh.get_mask_ids() (sempy/mesh.py:482-485), HOST ids. */
 int semb_set_mask(semb_ctx* ctx, const int64_t* mask_ids, int64_t n_mask);
+/* Mesh.setup_mask on the device (sempy/mesh.py:449-477): a node is a Dirichlet
+ * node when any coordinate lies within tol of the bounding box
+ * bbox6 = {xmin, xmax, ymin, ymax, zmin, zmax} (HOST array; the box of the WHOLE
+ * mesh when it is split over ranks).  Coordinates are (E*Np) arrays, `mem`. */
+int semb_setup_mask_box(semb_ctx* ctx, const double* xe, const double* ye, const double* ze, const double* bbox6,
+                        double tol, int mem);
+/* The mask as the reference stores it (mesh.mask): 0.0 at Dirichlet nodes, 1.0
+ * elsewhere, E*Np doubles. */
+int semb_get_mask(semb_ctx* ctx, double* mask, int mem);
+/* lo_hi[0] = min, lo_hi[1] = max of n doubles (bounding box of setup_mask,
+ * sempy/mesh.py:451-457); lo_hi is a HOST array. */
+int semb_minmax(int device, int64_t n, const double* x, double* lo_hi, int mem);
+/* Mesh.calc_geometric_factors (sempy/mesh.py:304-356) straight into the context:
+ * G = (grad a . grad b) * B * J from the coordinates (E*Np each, `mem`), B the
+ * tensor product of the GLL weights w[Nq] (HOST); jaco (optional, `mem`) receives
+ * the Jacobian.  Needs semb_set_derivative.  Nothing of G crosses PCIe. */
+int semb_setup_geom(semb_ctx* ctx, const double* w, const double* xe, const double* ye, const double* ze, double* jaco,
+                    int mem);
+/* Copy the six stored components (E,6,Np) out: mesh.get_geom(), sempy/mesh.py:514-517. */
+int semb_get_geom(semb_ctx* ctx, double* G6, int mem);
 /* Copy rmult (E*Np doubles) out; mesh.get_rmult(), sempy/mesh.py:511. */
 int semb_get_rmult(semb_ctx* ctx, double* rmult, int mem);
 
@@ -130,6 +155,14 @@ int semb_geom_factors(int device, int Nq, const double* D, const double* w, int6
  * verbose=1, elliptic.py:63-68). */
 int semb_cg(semb_ctx* ctx, const double* b, double* x, double tol, int maxit, int precond, int mem, int* niter,
             double* history);
+/* Fast-diagonalisation preconditioner for semb_cg(precond = SEMB_PRECOND_FDM), the
+ * multi-element form of the reference's sketch (example.py:71-114 eigenproblems,
+ * :155-171 fast_kron, :186-190 precon_fdm): per element interior
+ * (S(x)S(x)S) diag(scale/(ax l_a + ay l_b + az l_c)) (S(x)S(x)S)^T, point Jacobi on
+ * the element surfaces.  S: (Nq-2)^2 row-major [node][mode] eigenvectors of the
+ * interior 1-D problem A s = l B s with S^T B S = I; lambda: Nq-2 eigenvalues;
+ * elem_scale: (E,4) = ax, ay, az, scale per element.  All HOST arrays. */
+int semb_set_fdm(semb_ctx* ctx, const double* S, const double* lambda, const double* elem_scale);
 
 /* cg(A,b,...) / pcg(A,Minv,b,...) of sempy/iterative.py:4-42,45-85 for any
  * operator: the vector updates and dots run on the device, A and Minv are
@@ -144,8 +177,9 @@ int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_a
  * contiguous slab per rank (the reference is single-process: it hands gslib
  * comm = 0, sempy/mesh.py:437, and never partitions).  Nodes on the slab
  * interfaces have copies on several ranks: semb_gs / semb_ax(GS) / semb_cg
- * complete their sums with a neighbour exchange over NCCL (overlapped with the
- * interior elements inside semb_cg) and the CG dots with an all-reduce.
+ * complete their sums with a neighbour exchange (peer memory over NVLink once
+ * semb_p2p_attach has run, NCCL before that and as the fallback; overlapped with
+ * the interior elements inside semb_cg) and the CG dots with an all-reduce.
  *   semb_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller
  *     broadcasts it (torch.distributed, MPI, a file...).
  *   semb_comm_init: collective over all ranks.
@@ -178,16 +212,6 @@ int semb_set_halo(semb_ctx* ctx, int nneigh, const int* nb_rank, const int64_t* 
 int semb_p2p_alloc(semb_ctx* ctx, int64_t halo_capacity, char* handle64);
 int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv_off);
 
-/* Host-only helper (no device needed): the closure tables of the experimental fused operator +
- * gather-scatter kernel (tuning knob "ax_fused_gs", off by default), exposed so that the schedule can be
- * unit-tested on a CPU.  Segments are grouped by the element that holds their highest local index.
- * First call with base == NULL: sizes[0] = len(ids), sizes[1] = len(dep_elem), sizes[2] = number of
- * segments whose length is not 2, 4 or 8.  Second call fills base, dep_start (int32[E+1]), n2, n4, n8
- * (uint16[E]), ids and dep_elem. */
-int semb_host_closure_tables(int64_t E, int64_t Np, const int64_t* g2l, const int64_t* gstart, int64_t nglobal,
-                             int64_t* sizes, int32_t* base, uint16_t* n2, uint16_t* n4, uint16_t* n8, int32_t* ids,
-                             int32_t* dep_start, int32_t* dep_elem);
-
 /* ---- device memory helpers for callers without their own allocator ------ */
 int semb_malloc(int device, void** ptr, int64_t bytes);
 int semb_free(int device, void* ptr);
@@ -206,9 +230,10 @@ int semb_profile_get(semb_ctx* ctx, int kernel, double* total_ms, int64_t* launc
 int64_t semb_launch_count(semb_ctx* ctx);
 /* Process-wide tuning knobs for A/B measurements; results do not depend on
  * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
- * factors in the N = 7 Ax kernel.  "p2p": 1 (default) / 0, peer-memory transport
- * vs NCCL for the halo exchange and the scalar all-reduces.  "ax_fused_gs" (0) / "ax_fused_lag":
- * EXPERIMENTAL persistent operator + gather-scatter kernel inside semb_cg, not yet measured. */
+ * factors in the tuned Ax kernels.  "p2p": 1 (default) / 0, peer-memory transport
+ * vs NCCL for the halo exchange and the scalar all-reduces.  "gs_pull": 1 (default) / 0,
+ * gather-scatter summed inside its consumer (CG update kernel, out-of-place pass of
+ * semb_ax) vs the separate in-place pass. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

@@ -14,7 +14,7 @@ import numpy as np
 HOST, DEVICE = 0, 1
 G9, G6 = 9, 6
 AX_MASK, AX_GS = 1, 2
-PRECOND_NONE, PRECOND_JACOBI = 0, 1
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_FDM = 0, 1, 2
 K_AX, K_GS, K_UPDATE, K_DIRECTION = 0, 1, 2, 3
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsemb200.so")
@@ -35,8 +35,14 @@ SIGNATURES = {
     "semb_synchronize": (C.c_int, [C.c_void_p]),
     "semb_set_derivative": (C.c_int, [C.c_void_p, C.c_void_p]),
     "semb_set_geom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
-    "semb_set_gather_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "semb_set_gather_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "semb_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "semb_setup_mask_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
+    "semb_get_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_minmax": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_setup_geom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_get_geom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "semb_set_fdm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "semb_get_rmult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "semb_ax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "semb_gs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -78,11 +84,6 @@ SIGNATURES = {
     ),
     "semb_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),
     "semb_p2p_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
-    "semb_host_closure_tables": (
-        C.c_int,
-        [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
-    ),
     "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
     "semb_free": (C.c_int, [C.c_int, C.c_void_p]),
     "semb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
@@ -150,3 +151,46 @@ def current_device():
     if dev is not None:
         return int(dev)
     return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class DevBuf:
+    """Device array owned through semb_malloc / semb_free: the mesh keeps its node arrays (coordinates,
+    numbering, ...) here so that set-up never round-trips through the host.  ``__cuda_array_interface__``
+    lets torch / cupy wrap it without a copy (``torch.as_tensor(buf, device="cuda")``)."""
+
+    def __init__(self, shape, dtype, device=None):
+        self.shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.device = current_device() if device is None else device
+        self.size = int(np.prod(self.shape)) if self.shape else 1
+        self.nbytes = self.size * self.dtype.itemsize
+        handle = C.c_void_p()
+        check(lib().semb_malloc(self.device, C.byref(handle), max(self.nbytes, 1)))
+        self.ptr = handle.value
+
+    @classmethod
+    def from_host(cls, arr, dtype=None, device=None):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        buf = cls(arr.shape, arr.dtype, device)
+        if buf.nbytes:
+            check(lib().semb_memcpy(buf.device, buf.ptr, arr.ctypes.data, buf.nbytes, 0))
+        return buf
+
+    def to_host(self, count=None):
+        out = np.empty(self.shape, dtype=self.dtype)
+        nbytes = self.nbytes if count is None else int(count) * self.dtype.itemsize
+        if nbytes:
+            check(lib().semb_memcpy(self.device, out.ctypes.data, self.ptr, nbytes, 1))
+        return out if count is None else out.reshape(-1)[: int(count)]
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 2}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().semb_free(self.device, self.ptr)
+                self.ptr = None
+        except Exception:
+            pass

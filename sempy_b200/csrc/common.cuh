@@ -78,10 +78,6 @@ constexpr int kNumSMs = 148;  // B200
 struct DMat {
   double d[kMaxNq * kMaxNq];  // row-major, leading dimension Nq
 };
-// five private copies of D for the five phases of ax8_kernel (see line8x2)
-struct DMat8x {
-  double d[5][64];
-};
 
 // Device-resident scalars of one CG solve (no host round trip per iteration).
 struct CgScalars {
@@ -148,30 +144,29 @@ struct semb_ctx {
   int64_t gs_var_nseg = 0;
   int64_t gs_var_off = 0;
   bool have_gs = false;
-  // experimental fused operator + gather-scatter (ax8_fused.cuh): closure tables, work counters, flags
-  bool fused_ready = false;
-  int32_t *fz_base = nullptr, *fz_ids = nullptr, *fz_dep_start = nullptr, *fz_dep_elem = nullptr;
-  uint16_t *fz_n2 = nullptr, *fz_n4 = nullptr, *fz_n8 = nullptr;
-  unsigned int *fz_work = nullptr, *fz_flag = nullptr;
-  int* fz_err = nullptr;
-  unsigned int fz_tag = 0;
+  // pull form of the same schedule: link[q] = (len << 28) | offset of node q's segment in gs_ids, 0 for
+  // nodes without another local copy (and, once a halo is set, for nodes completed by the halo kernels)
+  uint32_t* gs_link = nullptr;
+  bool pull_ok = false;  // every segment has <= 15 copies and the id table is shorter than 2^28
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 
-  // Dirichlet mask: 1 bit per local node (1 = zeroed) + the id list
+  // Dirichlet mask: 1 bit per local node (1 = zeroed)
   uint32_t* maskbits = nullptr;
-  int64_t* mask_ids = nullptr;
-  int64_t n_mask = 0;
   bool have_mask = false;
 
   // scratch / CG state
-  double* partials = nullptr;  // per-CTA partial sums
+  double* partials = nullptr;   // per-CTA partial sums
+  double* partials2 = nullptr;  // per-group sums (reduce.cuh)
   int64_t partials_cap = 0;
-  unsigned int* ticket = nullptr;  // last-CTA-done counters
+  unsigned int* ticket = nullptr;         // group tickets of the grid reductions (reduce.cuh)
+  unsigned int* ticket_update = nullptr;  // the CG update kernel's own ticket (inside the same allocation)
+  int* info = nullptr;                    // 4 device ints for set-up checks
   semb::CgScalars* scal = nullptr;
   double* hist = nullptr;
   int64_t hist_cap = 0;
-  double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,stage
+  double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,scratch
+  double* stage[2] = {nullptr, nullptr};  // pooled staging of HOST vector arguments (never freed per call)
   int* h_pinned = nullptr;  // pinned {done, niter}
 
   // multi-GPU: NCCL communicator, interface ("halo") tables of this rank's element slab
@@ -204,6 +199,14 @@ struct semb_ctx {
   int64_t ll_halo_cap = 0;                 // doubles per parity in the halo part
   semb::HaloPeers halo_peers;              // neighbour ranks, my send blocks, where they land remotely
   unsigned int seq_scalar = 0, seq_halo = 0;  // host-side sequence numbers (same on all ranks)
+
+  // FDM preconditioner (fdm_kernels.cuh): 1-D eigenvectors / eigenvalues of the interior problem and the
+  // per-element scale factors
+  bool fdm_ready = false;
+  double* fdm_S = nullptr;     // [m*m S | m lambda], m = Nq - 2
+  double* fdm_invL = nullptr;  // (E, 4): ax, ay, az, scale
+  semb::DMat fdm_Sh;           // host copies for the kernel parameter block
+  double fdm_lam[semb::kMaxNq];
 
   semb::Profile prof;
   int64_t launch_count = 0;

@@ -11,7 +11,9 @@
 // Nq = 16; see line8x2 in ax_kernels.cuh for why) and read through uniform registers.
 #pragma once
 
-#include "ax_kernels.cuh"
+#include <cstring>
+
+#include "ax_common.cuh"
 
 namespace semb {
 
@@ -43,22 +45,20 @@ __device__ __forceinline__ void line_contract(const double (&D)[NQ * NQ], const 
   }
 }
 
-template <int NQ, bool MASK, bool DOT>
+template <int NQ, bool MASK, bool DOT, int DIR>
 __global__ void __launch_bounds__(AxlCfg<NQ>::NT, AxlCfg<NQ>::MINB)
-axl_kernel(const double* __restrict__ u, const double* __restrict__ G6, double* __restrict__ w,
-           const uint32_t* __restrict__ maskbits, double* __restrict__ partials, int64_t e0,
-           const __grid_constant__ DMatL<NQ> Dp, const int* __restrict__ done, int l2_prefetch) {
+axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> Dp) {
   using C = AxlCfg<NQ>;
   constexpr int NT = C::NT, NP = NQ * NQ * NQ, RS = C::RS, PS = C::PS;
-  if (done != nullptr && *done) return;
+  if (a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) double smem[];
-  __shared__ double s_part[(NT + 31) / 32];
   double* A = smem;
   double* B = smem + C::ARR;
   const int tid = threadIdx.x;
-  const int64_t e = e0 + blockIdx.x;
-  const double* ue = u + e * NP;
-  const double* ge = G6 + e * (int64_t)(6 * NP);
+  const int64_t e = a.e0 + blockIdx.x;
+  const double* ue = a.u + e * NP;
+  const double* ge = a.G6 + e * (int64_t)(6 * NP);
+  const int l2_prefetch = a.l2_prefetch;
 
   // bulk L2 prefetch of the element's block of G (see ax8_kernel)
   if (l2_prefetch) {
@@ -82,6 +82,20 @@ axl_kernel(const double* __restrict__ u, const double* __restrict__ G6, double* 
   double uc[NQ];
 #pragma unroll
   for (int k = 0; k < NQ; ++k) uc[k] = __ldg(ue + k * NT + t_g);
+  if (DIR != 0) {
+    // CG direction update folded into the load phase: p <- z + beta p, written back and used as u
+    const double beta = a.s->beta;
+    const double* re = a.r + e * NP;
+    const double* de = a.dinv + e * NP;
+    double* pe = a.p_out + e * NP;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      const double rv = __ldg(re + k * NT + t_g);
+      const double dv = DIR == 2 ? __ldg(de + k * NT + t_g) : 0.0;
+      uc[k] = dir_update<DIR>(uc[k], rv, dv, beta);
+      pe[k * NT + t_g] = uc[k];
+    }
+  }
   double g[6], gn[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) g[c] = __ldcs(ge + c * NP + t_g);
@@ -189,40 +203,47 @@ axl_kernel(const double* __restrict__ u, const double* __restrict__ G6, double* 
 
   // P5: sum the three parts, mask, local dot, store
   double dot = 0.0;
-  double* we = w + e * NP;
+  double* we = a.w + e * NP;
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
     double o = (A[k * PS + t_s] + B[k * PS + t_s]) + acc[k];
     if (MASK) {
       const int64_t gi = e * NP + k * NT + t_g;
-      if ((__ldg(maskbits + (gi >> 5)) >> (gi & 31)) & 1u) o = 0.0;
+      if ((__ldg(a.maskbits + (gi >> 5)) >> (gi & 31)) & 1u) o = 0.0;
     }
     if (DOT) dot = fma(o, uc[k], dot);
     we[k * NT + t_g] = o;
   }
   if (DOT) {
-    // NT need not be a multiple of 32: shuffles only inside full warps, the rest through shared memory
-    const int nfull = NT / 32;
-    if ((tid >> 5) < nfull) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if ((tid & 31) == 0) s_part[tid >> 5] = dot;
-    }
-    __syncthreads();
-    if (NT % 32 != 0 && tid >= nfull * 32) {
-      // the tail warp: serialised adds, fixed order
-      for (int q = nfull * 32; q < NT; ++q) {
-        if (tid == q) s_part[nfull] = (q == nfull * 32 ? 0.0 : s_part[nfull]) + dot;
-        __syncwarp(__activemask());
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int q = 0; q < (NT + 31) / 32; ++q) s += s_part[q];
-      partials[blockIdx.x] = s;
-    }
+    const double cta = block_sum_nt<NT>(dot);
+    double total;
+    if (grid_reduce<NT>(a.red, cta, a.cta_off + (int)blockIdx.x, a.ncta_total, total) && tid == 0) a.s->pAp = total;
   }
+}
+
+template <int NQ, bool MASK, bool DOT, int DIR>
+static int launch_axl_t(const AxArgs& a, const DMatL<NQ>& dl, cudaStream_t st, int device) {
+  using Cfg = AxlCfg<NQ>;
+  static bool attr_done[64] = {false};
+  if (!attr_done[device & 63]) {
+    SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, MASK, DOT, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, MASK, DOT, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done[device & 63] = true;
+  }
+  axl_kernel<NQ, MASK, DOT, DIR><<<(unsigned)(a.e1 - a.e0), Cfg::NT, Cfg::SMEM, st>>>(a, dl);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NQ>
+static int launch_axl_nq(const AxArgs& a, const DMat& D, bool mask, bool dot, int dir, cudaStream_t st, int device) {
+  DMatL<NQ> dl;
+  for (int q = 0; q < 5; ++q)
+    for (int r = 0; r < NQ; ++r) std::memcpy(&dl.d[q][r * NQ], &D.d[r * NQ], sizeof(double) * NQ);
+  SEMB_CHECK((dot && (dir == 1 || dir == 2)) || (!dot && dir == 0), "launch_axl: unsupported variant");
+  if (!dot) return mask ? launch_axl_t<NQ, true, false, 0>(a, dl, st, device) : launch_axl_t<NQ, false, false, 0>(a, dl, st, device);
+  if (dir == 1) return mask ? launch_axl_t<NQ, true, true, 1>(a, dl, st, device) : launch_axl_t<NQ, false, true, 1>(a, dl, st, device);
+  return mask ? launch_axl_t<NQ, true, true, 2>(a, dl, st, device) : launch_axl_t<NQ, false, true, 2>(a, dl, st, device);
 }
 
 }  // namespace semb

@@ -7,11 +7,10 @@
 #include <numeric>
 #include <utility>
 
-#include "ax8_fused.cuh"
-#include "ax_kernels.cuh"
-#include "axl_kernels.cuh"
-#include "closure_tables.h"
+#include "aux_kernels.cuh"
+#include "ax_common.cuh"
 #include "common.cuh"
+#include "fdm_kernels.cuh"
 #include "setup_kernels.cuh"
 #include "vec_kernels.cuh"
 
@@ -21,21 +20,18 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 // Tuning knobs for A/B measurements (environment at load time, or semb_set_tuning at run time).
-// None of them changes results.
+// None of them changes results beyond rounding (gs_pull: the same fixed summation order as the push form).
 static int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
   return v ? atoi(v) : fallback;
 }
 // "p2p": 0 = NCCL for the halo exchange and the scalar all-reduces instead of the peer-memory path
 static int g_p2p_on = env_int("SEMB_P2P", 1);
-// "ax_tuned_high_order": 0 = plane-sweep kernel for every order but N = 7
-static int g_ax_tuned_high_order = env_int("SEMB_AX_TUNED_HIGH_ORDER", 1);
-// "ax_fused_gs": 1 = EXPERIMENTAL persistent operator + gather-scatter kernel inside semb_cg (N = 7, one
-// GPU; ax8_fused.cuh); read when the gather-scatter schedule is built.  "ax_fused_lag": its closing lag.
-static int g_ax_fused_gs = env_int("SEMB_AX_FUSED_GS", 0);
-static int g_ax_fused_lag = env_int("SEMB_AX_FUSED_LAG", 2368);
 // "ax_l2_prefetch": 0 = no bulk L2 prefetch of G in the tuned Ax kernels
 static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
+// "gs_pull": 0 = separate in-place gather-scatter pass (push form) instead of summing the copies inside
+// the consumer (CG update kernel / out-of-place pull kernel)
+static int g_gs_pull = env_int("SEMB_GS_PULL", 1);
 
 const NcclApi& nccl() {
   static NcclApi api = [] {
@@ -97,7 +93,7 @@ struct ProfScope {
 };
 
 static int ensure_vec(semb_ctx* c, int which) {
-  if (c->vec[which] == nullptr) SEMB_CUDA(cudaMalloc(&c->vec[which], sizeof(double) * (size_t)std::max<int64_t>(c->n, 1)));
+  if (c->vec[which] == nullptr) SEMB_CUDA(cudaMalloc(&c->vec[which], sizeof(double) * (size_t)std::max<int64_t>(c->n, 2)));
   return 0;
 }
 
@@ -106,119 +102,53 @@ static int bind_device(semb_ctx* c) {
   return 0;
 }
 
-// ---- K1 dispatch -----------------------------------------------------------
-template <int NQ>
-static int launch_ax_generic(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
-                             const int* done, int64_t part_off) {
-  const unsigned grid = (unsigned)(e1 - e0);
-  const uint32_t* mb = c->maskbits;
-#define SEMB_LAUNCH_G(M, DT) \
-  ax_generic_kernel<NQ, M, DT><<<grid, NQ * NQ, 0, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, c->D, done)
-  if (mask && dot) SEMB_LAUNCH_G(true, true);
-  else if (mask) SEMB_LAUNCH_G(true, false);
-  else if (dot) SEMB_LAUNCH_G(false, true);
-  else SEMB_LAUNCH_G(false, false);
-#undef SEMB_LAUNCH_G
-  SEMB_CUDA(cudaGetLastError());
-  return 0;
-}
+// 128-bit accesses of the vector kernels need 16-byte aligned device vectors (a contiguous torch view
+// with an odd element offset is not): refuse instead of faulting inside a kernel.
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// K1 for Nq = 9..16 (axl_kernels.cuh): one CTA per element
-template <int NQ>
-static int launch_axl(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
-                      const int* done, int64_t part_off) {
-  using Cfg = AxlCfg<NQ>;
-  static bool attr_done[64] = {false};
-  DMatL<NQ> dl;
-  for (int q = 0; q < 5; ++q)
-    for (int r = 0; r < NQ; ++r) std::memcpy(&dl.d[q][r * NQ], &c->D.d[r * NQ], sizeof(double) * NQ);
-  if (!attr_done[c->device & 63]) {
-#define SEMB_ATTR(M, DT)                                                                                                  \
-  SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, M, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); \
-  SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, M, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SEMB_ATTR(true, true) SEMB_ATTR(true, false) SEMB_ATTR(false, true) SEMB_ATTR(false, false)
-#undef SEMB_ATTR
-    attr_done[c->device & 63] = true;
+static void drop_jacobi(semb_ctx* c) {
+  if (c->vec[4]) {  // cached Jacobi diagonal is stale
+    cudaFree(c->vec[4]);
+    c->vec[4] = nullptr;
   }
-  const unsigned grid = (unsigned)(e1 - e0);
-#define SEMB_LAUNCH_L(M, DT)                                                                                     \
-  axl_kernel<NQ, M, DT><<<grid, Cfg::NT, Cfg::SMEM, c->stream>>>(p, c->G6, ap, c->maskbits, c->partials + part_off, e0, dl, \
-                                                                done, g_ax_l2_prefetch)
-  if (mask && dot) SEMB_LAUNCH_L(true, true);
-  else if (mask) SEMB_LAUNCH_L(true, false);
-  else if (dot) SEMB_LAUNCH_L(false, true);
-  else SEMB_LAUNCH_L(false, false);
-#undef SEMB_LAUNCH_L
-  SEMB_CUDA(cudaGetLastError());
-  return 0;
+  c->fdm_ready = false;
 }
 
-// Number of per-CTA dot partials the Ax launch over [e0,e1) writes.
-static int64_t ax_num_partials(const semb_ctx* c, int64_t e0, int64_t e1) {
-  if (c->Nq == 8) return (e1 - e0 + AX8_WARPS - 1) / AX8_WARPS;
-  return e1 - e0;
-}
-
-static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int64_t e0, int64_t e1,
-                     const int* done, int64_t part_off = 0) {
+// ---- K1 dispatch -----------------------------------------------------------
+// One launch over the elements [e0, e1).  dot: the launch is part of a logical grid of ncta_total CTAs
+// whose fixed-order sum of p.Ap ends up in s->pAp (reduce.cuh); dir: 1 / 2 fold the CG direction update
+// p <- r + beta p / p <- dinv r + beta p into the load phase.
+static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int dir, int64_t e0, int64_t e1,
+                     const double* r, const double* dinv, int cta_off, int ncta_total, const int* done) {
   if (e1 <= e0) return 0;
   ProfScope ps(c, SEMB_K_AX);
   c->launch_count++;
-  if (c->Nq == 8) {
-    static bool attr_done[64] = {false};
-    DMat8x d8;
-    for (int q = 0; q < 5; ++q) std::memcpy(d8.d[q], c->D.d, sizeof(d8.d[q]));
-    const unsigned grid = (unsigned)((e1 - e0 + AX8_WARPS - 1) / AX8_WARPS);
-    const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(c->maskbits);
-    if (!attr_done[c->device & 63]) {
-#define SEMB_ATTR(M, DT)                                                                                     \
-  SEMB_CUDA(cudaFuncSetAttribute(ax8_kernel<M, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX8_SMEM)); \
-  SEMB_CUDA(cudaFuncSetAttribute(ax8_kernel<M, DT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      SEMB_ATTR(true, true) SEMB_ATTR(true, false) SEMB_ATTR(false, true) SEMB_ATTR(false, false)
-#undef SEMB_ATTR
-      attr_done[c->device & 63] = true;
-    }
-#define SEMB_LAUNCH_8(M, DT) \
-  ax8_kernel<M, DT><<<grid, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(p, c->G6, ap, mb, c->partials + part_off, e0, e1, d8, done, g_ax_l2_prefetch)
-    if (mask && dot) SEMB_LAUNCH_8(true, true);
-    else if (mask) SEMB_LAUNCH_8(true, false);
-    else if (dot) SEMB_LAUNCH_8(false, true);
-    else SEMB_LAUNCH_8(false, false);
-#undef SEMB_LAUNCH_8
-    SEMB_CUDA(cudaGetLastError());
-    return 0;
-  }
-  if (g_ax_tuned_high_order) {
-    // N = 8 ... 15 (the reference's test order N = 10, BASELINE config 3 at N = 15): tuned kernel
-    switch (c->Nq) {
-#define SEMB_CASE_L(Q) \
-  case Q:              \
-    return launch_axl<Q>(c, p, ap, mask, dot, e0, e1, done, part_off);
-      SEMB_CASE_L(9) SEMB_CASE_L(10) SEMB_CASE_L(11) SEMB_CASE_L(12) SEMB_CASE_L(13) SEMB_CASE_L(14) SEMB_CASE_L(15)
-      SEMB_CASE_L(16)
-#undef SEMB_CASE_L
-      default:
-        break;
-    }
-  }
-  switch (c->Nq) {
-#define SEMB_CASE(Q) \
-  case Q:            \
-    return launch_ax_generic<Q>(c, p, ap, mask, dot, e0, e1, done, part_off);
-    SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(9) SEMB_CASE(10)
-    SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
-#undef SEMB_CASE
-    default:
-      set_error("semb_ax: unsupported Nq " + std::to_string(c->Nq));
-      return 2;
-  }
+  AxArgs a;
+  a.u = p;
+  a.p_out = const_cast<double*>(p);
+  a.r = r;
+  a.dinv = dinv;
+  a.G6 = c->G6;
+  a.w = ap;
+  a.maskbits = c->maskbits;
+  a.s = c->scal;
+  a.done = done;
+  a.red = GridRed{c->partials, c->partials2, c->ticket};
+  a.cta_off = cta_off;
+  a.ncta_total = ncta_total;
+  a.e0 = e0;
+  a.e1 = e1;
+  a.l2_prefetch = g_ax_l2_prefetch;
+  if (c->Nq == 8) return launch_ax8(a, c->D, mask, dot, dir, c->stream, c->device);
+  if (c->Nq >= 9) return launch_axl(c->Nq, a, c->D, mask, dot, dir, c->stream, c->device);
+  return launch_ax_generic(c->Nq, a, c->D, mask, dot, dir, c->stream);
 }
 
 // ---- K2 dispatch -----------------------------------------------------------
-static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_src = nullptr, int64_t red_n = 0,
-                     double* red_out = nullptr) {
+// in-place (push) form
+static int launch_gs(semb_ctx* c, double* x, const int* done) {
   ProfScope ps(c, SEMB_K_GS);
-  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0, red_src, red_n, red_out};
+  GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
     if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
     else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
@@ -233,7 +163,7 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_
   plan.b2 = blocks_for(plan.n2, 4);
   plan.b4 = blocks_for(plan.n4, 2);
   plan.b8 = blocks_for(plan.n8, 1);
-  const int total_blocks = plan.b2 + plan.b4 + plan.b8 + (red_out != nullptr ? 1 : 0);
+  const int total_blocks = plan.b2 + plan.b4 + plan.b8;
   if (total_blocks > 0) {
     c->launch_count++;
     gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
@@ -247,37 +177,15 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, const double* red_
   }
   return 0;
 }
-
-// EXPERIMENTAL fused operator + gather-scatter (see ax8_fused.cuh); mask + dot variant only
-static int launch_ax_fused(semb_ctx* c, const double* p, double* ap, double* dot_out, const int* done) {
-  ProfScope ps(c, SEMB_K_AX);
-  static bool attr_done[64] = {false};
-  if (!attr_done[c->device & 63]) {
-    SEMB_CUDA(cudaFuncSetAttribute(ax8_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX8_SMEM));
-    SEMB_CUDA(cudaFuncSetAttribute(ax8_fused_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done[c->device & 63] = true;
-  }
-  DMat8x d8;
-  for (int q = 0; q < 5; ++q) std::memcpy(d8.d[q], c->D.d, sizeof(d8.d[q]));
-  FusedGsTables gt{c->fz_base, c->fz_n2, c->fz_n4, c->fz_n8, c->fz_ids, c->fz_dep_start, c->fz_dep_elem};
-  const int lag = std::max(1, g_ax_fused_lag);
-  c->fz_tag++;
+// out-of-place (pull) form: out = dssum(in) over the local copies
+static int launch_gs_pull(semb_ctx* c, const double* in, double* out) {
+  ProfScope ps(c, SEMB_K_GS);
   c->launch_count++;
-  ax8_fused_kernel<true, true><<<kNumSMs * 4, AX8_WARPS * 32, AX8_SMEM, c->stream>>>(
-      p, c->G6, ap, reinterpret_cast<const unsigned long long*>(c->maskbits), c->partials, dot_out, (int)c->E, d8, done, gt,
-      c->fz_work, c->fz_flag, c->fz_tag, lag, c->fz_err);
+  gs_pull_kernel<<<vec_grid(c->n / 2 + 1), VEC_NT, 0, c->stream>>>(in, out, c->gs_link, c->gs_ids, c->n);
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
-static int launch_gs_var_only(semb_ctx* c, double* x, const int* done) {
-  if (c->gs_var_nseg > 0) {
-    c->launch_count++;
-    gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
-                                                                      c->gs_var_nseg, done);
-    SEMB_CUDA(cudaGetLastError());
-  }
-  return 0;
-}
+static inline bool use_pull(const semb_ctx* c) { return c->pull_ok && g_gs_pull; }
 
 // ---- multi-GPU halo --------------------------------------------------------
 static inline bool use_p2p(const semb_ctx* c) { return c->p2p && g_p2p_on; }
@@ -293,6 +201,10 @@ static HaloPeers make_halo_peers(const semb_ctx* c, const std::vector<int64_t>& 
   }
   hp.off[hp.nneigh] = c->n_send;
   return hp;
+}
+
+static LlArgs ll_args(semb_ctx* c, unsigned int seq) {
+  return LlArgs{c->ll_peer_dev, c->rank, c->nranks, seq, c->ll_error};
 }
 
 // gather this rank's partial sums; with the peer-memory path this also delivers them (seq = the
@@ -321,21 +233,29 @@ static int halo_exchange(semb_ctx* c, cudaStream_t st) {
   SEMB_NCCL(GroupEnd());
   return 0;
 }
-static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done) {
-  if (c->n_if == 0) return 0;
-  c->launch_count++;
+// pass_vals (peer-memory path only): scalars all-reduced by a passenger CTA of the same launch
+static int halo_scatter(semb_ctx* c, double* x, cudaStream_t st, const int* done, double* pass_vals = nullptr,
+                        int pass_count = 0) {
   if (use_p2p(c)) {
-    halo_scatter_p2p_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->ll_local + LL_SCALAR_WORDS, c->n_send,
-                                                                  c->src_start, c->src_off, c->copy_start, c->copy_ids,
-                                                                  c->n_if, c->ll_halo_cap, c->seq_halo, done, c->ll_error);
+    if (c->n_if == 0 && pass_vals == nullptr) return 0;
+    unsigned int pseq = 0;
+    if (pass_vals != nullptr) pseq = ++c->seq_scalar;
+    const int blocks = (c->n_if > 0 ? vec_grid(c->n_if) : 0) + (pass_vals != nullptr ? 1 : 0);
+    c->launch_count++;
+    halo_scatter_p2p_kernel<<<blocks, VEC_NT, 0, st>>>(x, c->hbuf, c->ll_local + LL_SCALAR_WORDS, c->n_send, c->src_start,
+                                                       c->src_off, c->copy_start, c->copy_ids, c->n_if, c->ll_halo_cap,
+                                                       c->seq_halo, done, c->ll_error, pass_vals, pass_count,
+                                                       ll_args(c, pseq));
   } else {
+    if (c->n_if == 0) return 0;
+    c->launch_count++;
     halo_scatter_kernel<<<vec_grid(c->n_if), VEC_NT, 0, st>>>(x, c->hbuf, c->src_start, c->src_off, c->copy_start,
                                                              c->copy_ids, c->n_if, done);
   }
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
-// Complete gather-scatter of one vector on the context's stream (no overlap).
+// Complete in-place gather-scatter of one vector on the context's stream (no overlap).
 static int gs_full(semb_ctx* c, double* x, const int* done) {
   if (c->have_halo) {
     c->seq_halo++;
@@ -379,31 +299,39 @@ static int reduce_partials(semb_ctx* c, int64_t n, int64_t stride, int nout, dou
   return 0;
 }
 
+// partial sums, group sums and tickets of the grid reductions (reduce.cuh); the CG update kernel's own
+// ticket is the last entry
 static int ensure_partials(semb_ctx* c) {
   const int64_t need = std::max<int64_t>(c->E, 2 * (int64_t)kNumSMs * 8) + 16;
   if (c->partials_cap < need) {
-    if (c->partials) cudaFree(c->partials);
+    cudaFree(c->partials);
+    cudaFree(c->partials2);
+    cudaFree(c->ticket);
+    const int64_t groups = need / RED_GROUP + 2;
     SEMB_CUDA(cudaMalloc(&c->partials, sizeof(double) * (size_t)need));
+    SEMB_CUDA(cudaMalloc(&c->partials2, sizeof(double) * (size_t)groups));
+    SEMB_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int) * (size_t)(groups + 2)));
+    SEMB_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int) * (size_t)(groups + 2)));
     c->partials_cap = need;
+    c->ticket_update = c->ticket + groups + 1;
   }
   return 0;
 }
 
-// Host <-> device staging of caller vectors.
+// Host <-> device staging of caller vectors through two pooled buffers of the context (allocated on
+// first use, kept): a reference-style loop that calls mesh.dssum(x) with NumPy arrays pays two copies per
+// call, not an allocation.
 struct Staged {
   double* dev = nullptr;
-  bool owned = false;
-  ~Staged() {
-    if (owned && dev) cudaFree(dev);
-  }
 };
-static int stage_in(semb_ctx* c, const double* src, int mem, int64_t n, Staged& s, bool copy) {
+static int stage_in(semb_ctx* c, const double* src, int mem, int64_t n, Staged& s, bool copy, int slot) {
   if (mem == SEMB_DEVICE) {
+    SEMB_CHECK(aligned16(src), "device vectors must be 16-byte aligned (a tensor view with an odd element offset is not)");
     s.dev = const_cast<double*>(src);
     return 0;
   }
-  SEMB_CUDA(cudaMalloc(&s.dev, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
-  s.owned = true;
+  if (c->stage[slot] == nullptr) SEMB_CUDA(cudaMalloc(&c->stage[slot], sizeof(double) * (size_t)std::max<int64_t>(c->n, 2)));
+  s.dev = c->stage[slot];
   if (copy) SEMB_CUDA(cudaMemcpyAsync(s.dev, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
@@ -418,16 +346,17 @@ static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
 static int build_rmult(semb_ctx* c) {
   if (!c->rmult) SEMB_CUDA(cudaMalloc(&c->rmult, sizeof(double) * (size_t)c->n));
   if (!c->mult) SEMB_CUDA(cudaMalloc(&c->mult, (size_t)c->n + 16));
+  SEMB_CUDA(cudaMemsetAsync(c->info, 0, 4 * sizeof(int), c->stream));
   fill_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, 1.0, c->n);
   SEMB_TRY(gs_full(c, c->rmult, nullptr));
-  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->mult, c->n);
+  reciprocal_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->rmult, c->mult, c->n, c->info);
   SEMB_CUDA(cudaGetLastError());
+  int info[4] = {0, 0, 0, 0};
+  SEMB_CUDA(cudaMemcpyAsync(info, c->info, sizeof(info), cudaMemcpyDeviceToHost, c->stream));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   SEMB_TRY(check_ll_error(c));
-  if (c->vec[4]) {  // cached Jacobi diagonal is stale
-    cudaFree(c->vec[4]);
-    c->vec[4] = nullptr;
-  }
+  SEMB_CHECK(info[0] == 0, "gather-scatter: a node has more than 255 copies (the CG update kernel stores one byte per node)");
+  drop_jacobi(c);
   return 0;
 }
 
@@ -456,13 +385,37 @@ static int upload(T** dst, const T* src, size_t count) {
   return 0;
 }
 
+// scoped device allocation for set-up temporaries
+struct DevTmp {
+  void* p = nullptr;
+  ~DevTmp() { cudaFree(p); }
+  int alloc(size_t bytes) {
+    SEMB_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    return 0;
+  }
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+// HOST arrays are uploaded into a temporary, DEVICE arrays used in place
+template <typename T>
+static int dev_view(const T* src, int mem, size_t count, DevTmp& tmp, const T** out) {
+  if (mem == SEMB_DEVICE) {
+    *out = src;
+    return 0;
+  }
+  SEMB_TRY(tmp.alloc(sizeof(T) * count));
+  SEMB_CUDA(cudaMemcpy(tmp.p, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+  *out = tmp.as<T>();
+  return 0;
+}
+
 }  // namespace semb
 
 using namespace semb;
 
 extern "C" {
 
-int semb_version(void) { return 100; }
+int semb_version(void) { return 200; }
 const char* semb_last_error(void) { return g_last_error.c_str(); }
 
 int semb_device_count(void) {
@@ -491,8 +444,8 @@ int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq) {
   SEMB_CUDA(cudaMalloc(&c->scal, sizeof(CgScalars) + 8 * sizeof(double)));
   SEMB_CUDA(cudaMemset(c->scal, 0, sizeof(CgScalars) + 8 * sizeof(double)));
   SEMB_CUDA(cudaMallocHost(&c->h_pinned, 64));
-  SEMB_CUDA(cudaMalloc(&c->ticket, 4 * sizeof(unsigned int)));
-  SEMB_CUDA(cudaMemset(c->ticket, 0, 4 * sizeof(unsigned int)));
+  SEMB_CUDA(cudaMalloc(&c->info, 4 * sizeof(int)));
+  SEMB_CUDA(cudaMemset(c->info, 0, 4 * sizeof(int)));
   if (ensure_partials(c)) return 1;
   SEMB_CUDA(cudaDeviceSynchronize());  // the memsets above ran on the default stream
   *out = c;
@@ -505,26 +458,21 @@ int semb_destroy(semb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->G6);
   cudaFree(c->gs_ids);
+  cudaFree(c->gs_link);
   cudaFree(c->gs_var_start);
   cudaFree(c->rmult);
   cudaFree(c->mult);
   cudaFree(c->maskbits);
-  cudaFree(c->mask_ids);
   cudaFree(c->partials);
+  cudaFree(c->partials2);
   cudaFree(c->scal);
   cudaFree(c->ticket);
-  cudaFree(c->fz_base);
-  cudaFree(c->fz_n2);
-  cudaFree(c->fz_n4);
-  cudaFree(c->fz_n8);
-  cudaFree(c->fz_ids);
-  cudaFree(c->fz_dep_start);
-  cudaFree(c->fz_dep_elem);
-  cudaFree(c->fz_work);
-  cudaFree(c->fz_flag);
-  cudaFree(c->fz_err);
+  cudaFree(c->info);
   cudaFree(c->hist);
+  cudaFree(c->fdm_S);
+  cudaFree(c->fdm_invL);
   for (double* v : c->vec) cudaFree(v);
+  for (double* v : c->stage) cudaFree(v);
   cudaFreeHost(c->h_pinned);
   for (int k = 0; k < SEMB_K_COUNT; ++k) {
     for (cudaEvent_t e : c->prof.start[k]) cudaEventDestroy(e);
@@ -570,6 +518,7 @@ int semb_set_derivative(semb_ctx* c, const double* D) {
   std::memset(c->D.d, 0, sizeof(c->D.d));
   std::memcpy(c->D.d, D, sizeof(double) * c->Nq * c->Nq);
   c->have_D = true;
+  drop_jacobi(c);
   return 0;
 }
 
@@ -614,89 +563,148 @@ int semb_set_geom(semb_ctx* c, const double* G, int layout, int mem) {
   }
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   c->have_G = true;
+  drop_jacobi(c);
   return 0;
 }
 
-int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gstart, int64_t nglobal) {
-  SEMB_CHECK(c && g2l && gstart, "semb_set_gather_scatter: NULL argument");
-  SEMB_CHECK(nglobal > 0 && gstart[0] == 0 && gstart[nglobal] == c->n,
-             "semb_set_gather_scatter: global_start must run from 0 to E*Np");
+int semb_setup_geom(semb_ctx* c, const double* w, const double* xe, const double* ye, const double* ze, double* jaco,
+                    int mem) {
+  SEMB_CHECK(c && w && xe && ye && ze, "semb_setup_geom: NULL argument");
+  SEMB_CHECK(c->have_D, "semb_setup_geom: call semb_set_derivative first");
   SEMB_TRY(bind_device(c));
-  // Classify the segments with more than one local copy by length.
-  std::vector<std::pair<int32_t, int64_t>> cls[4];  // len 2, 4, 8, other : (first local id, segment)
-  for (int64_t s = 0; s < nglobal; ++s) {
-    const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
-    SEMB_CHECK(len >= 1, "semb_set_gather_scatter: empty segment");
-    if (len == 1) continue;
-    int64_t first = g2l[lo];
-    for (int64_t q = lo + 1; q < lo + len; ++q) first = std::min(first, g2l[q]);
-    SEMB_CHECK(first >= 0 && first < c->n, "semb_set_gather_scatter: local index out of range");
-    const int k = len == 2 ? 0 : len == 4 ? 1 : len == 8 ? 2 : 3;
-    cls[k].emplace_back((int32_t)first, s);
+  DMat wm;
+  std::memset(wm.d, 0, sizeof(wm.d));
+  std::memcpy(wm.d, w, sizeof(double) * c->Nq);
+  const size_t cnt = (size_t)c->n;
+  DevTmp tx, ty, tz, tj;
+  const double *dx, *dy, *dz;
+  SEMB_TRY(dev_view(xe, mem, cnt, tx, &dx));
+  SEMB_TRY(dev_view(ye, mem, cnt, ty, &dy));
+  SEMB_TRY(dev_view(ze, mem, cnt, tz, &dz));
+  double* dj = jaco;
+  if (jaco != nullptr && mem == SEMB_HOST) {
+    SEMB_TRY(tj.alloc(sizeof(double) * cnt));
+    dj = tj.as<double>();
   }
-  // Order segments by their first local index so that neighbouring threads touch neighbouring
-  // memory -- DESCENDING: the operator kernel before the gather-scatter writes its output in ascending
-  // element order, so its tail is what is still in L2; walking backwards reads that first, and leaves
-  // the head of the vector in L2 for the ascending update kernel that follows.
-  for (auto& v : cls) std::sort(v.begin(), v.end(), [](const std::pair<int32_t, int64_t>& a, const std::pair<int32_t, int64_t>& b) { return a > b; });
-  std::vector<int32_t> ids;
-  std::vector<int32_t> var_start;
-  c->gs_classes.clear();
-  const int lens[3] = {2, 4, 8};
-  auto emit = [&](int64_t s) {
-    const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
-    const size_t at = ids.size();
-    for (int64_t q = lo; q < lo + len; ++q) ids.push_back((int32_t)g2l[q]);
-    std::sort(ids.begin() + at, ids.end());  // fixed summation order: ascending local index
-  };
-  for (int k = 0; k < 3; ++k) {
-    while (ids.size() % 4) ids.push_back(0);
-    GsClass gc{lens[k], (int64_t)cls[k].size(), (int64_t)ids.size()};
-    for (auto& pr : cls[k]) emit(pr.second);
-    c->gs_classes.push_back(gc);
-  }
-  while (ids.size() % 4) ids.push_back(0);
-  c->gs_var_off = (int64_t)ids.size();
-  c->gs_var_nseg = (int64_t)cls[3].size();
-  var_start.push_back(0);
-  for (auto& pr : cls[3]) {
-    emit(pr.second);
-    var_start.push_back((int32_t)(ids.size() - c->gs_var_off));
-  }
-  c->gs_nids = (int64_t)ids.size();
-  cudaFree(c->gs_ids);
+  if (!c->G6) SEMB_CUDA(cudaMalloc(&c->G6, sizeof(double) * 6 * cnt));
+  const int Np = (int)c->Np;
+  SEMB_CUDA(cudaFuncSetAttribute(geom_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 4096)));
+  geom_factors_kernel<<<(unsigned)c->E, std::min(256, ((Np + 31) / 32) * 32), sizeof(double) * 3 * Np, c->stream>>>(
+      dx, dy, dz, c->G6, dj, c->Nq, c->D, wm);
+  SEMB_CUDA(cudaGetLastError());
+  if (jaco != nullptr && mem == SEMB_HOST)
+    SEMB_CUDA(cudaMemcpyAsync(jaco, dj, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_G = true;
+  drop_jacobi(c);
+  return 0;
+}
+
+int semb_get_geom(semb_ctx* c, double* G6, int mem) {
+  SEMB_CHECK(c && G6, "semb_get_geom: NULL argument");
+  SEMB_CHECK(c->have_G, "semb_get_geom: geometric factors are not set");
+  SEMB_TRY(bind_device(c));
+  SEMB_CUDA(cudaMemcpyAsync(G6, c->G6, sizeof(double) * 6 * (size_t)c->n,
+                            mem == SEMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gstart, int64_t nglobal, int mem) {
+  SEMB_CHECK(c && g2l && gstart, "semb_set_gather_scatter: NULL argument");
+  SEMB_CHECK(nglobal > 0 && nglobal <= c->n, "semb_set_gather_scatter: nglobal out of range");
+  SEMB_TRY(bind_device(c));
+  const int64_t n = c->n, ns = nglobal;
+  DevTmp t_g2l, t_gst;
+  const int64_t *d_g2l, *d_gst;
+  SEMB_TRY(dev_view(g2l, mem, (size_t)n, t_g2l, &d_g2l));
+  SEMB_TRY(dev_view(gstart, mem, (size_t)ns + 1, t_gst, &d_gst));
+  int64_t ends[2] = {-1, -1};
+  SEMB_CUDA(cudaMemcpy(&ends[0], d_gst, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SEMB_CUDA(cudaMemcpy(&ends[1], d_gst + ns, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SEMB_CHECK(ends[0] == 0 && ends[1] == n, "semb_set_gather_scatter: global_start must run from 0 to E*Np");
+
+  // 1. one sort key per segment: (length class, lowest local index)
+  DevTmp k0, k1, v0, v1, info, bounds, cubtmp, vlen, vstart;
+  SEMB_TRY(k0.alloc(8 * (size_t)ns));
+  SEMB_TRY(k1.alloc(8 * (size_t)ns));
+  SEMB_TRY(v0.alloc(4 * (size_t)ns));
+  SEMB_TRY(v1.alloc(4 * (size_t)ns));
+  SEMB_TRY(info.alloc(4 * sizeof(int)));
+  SEMB_TRY(bounds.alloc(5 * sizeof(int64_t)));
+  SEMB_CUDA(cudaMemset(info.p, 0, 4 * sizeof(int)));
+  seg_keys_kernel<<<vec_grid(ns), VEC_NT>>>(d_g2l, d_gst, ns, n, k0.as<unsigned long long>(), v0.as<int32_t>(), info.as<int>());
+  SEMB_CUDA(cudaGetLastError());
+  size_t tb = 0;
+  SEMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(),
+                                            v0.as<int32_t>(), v1.as<int32_t>(), (int)ns, 0, 43));
+  SEMB_TRY(cubtmp.alloc(tb));
+  SEMB_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, k0.as<unsigned long long>(), k1.as<unsigned long long>(),
+                                            v0.as<int32_t>(), v1.as<int32_t>(), (int)ns, 0, 43));
+  seg_bounds_kernel<<<1, 32>>>(k1.as<unsigned long long>(), ns, bounds.as<int64_t>());
+  SEMB_CUDA(cudaGetLastError());
+  SegLayout lay;
+  int h_info[4];
+  SEMB_CUDA(cudaMemcpy(lay.b, bounds.p, sizeof(lay.b), cudaMemcpyDeviceToHost));
+  SEMB_CUDA(cudaMemcpy(h_info, info.p, sizeof(h_info), cudaMemcpyDeviceToHost));
+  SEMB_CHECK((h_info[0] & 1) == 0, "semb_set_gather_scatter: empty segment or offsets out of range");
+  SEMB_CHECK((h_info[0] & 2) == 0, "semb_set_gather_scatter: local index out of range");
+  const int32_t* sorted = v1.as<int32_t>();
+
+  // 2. layout of the id table: [len 2 | len 4 | len 8 | other], every class starting at a multiple of 4
+  const int64_t n2 = lay.b[1] - lay.b[0], n4 = lay.b[2] - lay.b[1], n8 = lay.b[3] - lay.b[2], nv = lay.b[4] - lay.b[3];
+  auto align4 = [](int64_t v) { return (v + 3) & ~(int64_t)3; };
+  lay.off[0] = 0;
+  lay.off[1] = align4(lay.off[0] + 2 * n2);
+  lay.off[2] = align4(lay.off[1] + 4 * n4);
+  lay.off[3] = align4(lay.off[2] + 8 * n8);
+  int64_t nvar_ids = 0;
   cudaFree(c->gs_var_start);
-  c->gs_ids = nullptr;
   c->gs_var_start = nullptr;
-  SEMB_CUDA(cudaMalloc(&c->gs_ids, sizeof(int32_t) * std::max<size_t>(ids.size(), 4)));
-  SEMB_CUDA(cudaMemcpy(c->gs_ids, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
-  SEMB_CUDA(cudaMalloc(&c->gs_var_start, sizeof(int32_t) * var_start.size()));
-  SEMB_CUDA(cudaMemcpy(c->gs_var_start, var_start.data(), sizeof(int32_t) * var_start.size(), cudaMemcpyHostToDevice));
-  SEMB_CUDA(cudaDeviceSynchronize());  // uploads done before the context's (non-blocking) stream uses them
-  c->have_gs = true;
-  c->fused_ready = false;
-  if (g_ax_fused_gs && c->Nq == 8) {
-    ClosureTables t;
-    SEMB_CHECK(build_closure_tables(c->E, c->Np, g2l, gstart, nglobal, t) == 0, "semb_set_gather_scatter: closure tables failed");
-    SEMB_TRY(upload(&c->fz_base, t.base.data(), t.base.size()));
-    SEMB_TRY(upload(&c->fz_n2, t.n2.data(), t.n2.size()));
-    SEMB_TRY(upload(&c->fz_n4, t.n4.data(), t.n4.size()));
-    SEMB_TRY(upload(&c->fz_n8, t.n8.data(), t.n8.size()));
-    SEMB_TRY(upload(&c->fz_ids, t.ids.data(), t.ids.size()));
-    SEMB_TRY(upload(&c->fz_dep_start, t.dep_start.data(), t.dep_start.size()));
-    SEMB_TRY(upload(&c->fz_dep_elem, t.dep_elem.data(), t.dep_elem.size()));
-    if (!c->fz_work) {
-      SEMB_CUDA(cudaMalloc(&c->fz_work, 4 * sizeof(unsigned int)));
-      SEMB_CUDA(cudaMalloc(&c->fz_flag, sizeof(unsigned int) * (size_t)c->E));
-      SEMB_CUDA(cudaMalloc(&c->fz_err, sizeof(int)));
-    }
-    SEMB_CUDA(cudaMemset(c->fz_work, 0, 4 * sizeof(unsigned int)));
-    SEMB_CUDA(cudaMemset(c->fz_flag, 0, sizeof(unsigned int) * (size_t)c->E));
-    SEMB_CUDA(cudaMemset(c->fz_err, 0, sizeof(int)));
-    SEMB_CUDA(cudaDeviceSynchronize());
-    c->fz_tag = 0;
-    c->fused_ready = true;
+  SEMB_CUDA(cudaMalloc(&c->gs_var_start, sizeof(int32_t) * (size_t)(nv + 1)));
+  if (nv > 0) {
+    SEMB_TRY(vlen.alloc(sizeof(int32_t) * (size_t)(nv + 1)));
+    SEMB_CUDA(cudaMemset(vlen.p, 0, sizeof(int32_t) * (size_t)(nv + 1)));
+    seg_var_len_kernel<<<vec_grid(nv), VEC_NT>>>(sorted, d_gst, lay.b[3], lay.b[4], vlen.as<int32_t>());
+    SEMB_CUDA(cudaGetLastError());
+    size_t sb = 0;
+    SEMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, vlen.as<int32_t>(), c->gs_var_start, (int)(nv + 1)));
+    DevTmp scantmp;
+    SEMB_TRY(scantmp.alloc(sb));
+    SEMB_CUDA(cub::DeviceScan::ExclusiveSum(scantmp.p, sb, vlen.as<int32_t>(), c->gs_var_start, (int)(nv + 1)));
+    int32_t last = 0;
+    SEMB_CUDA(cudaMemcpy(&last, c->gs_var_start + nv, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    nvar_ids = last;
+  } else {
+    SEMB_CUDA(cudaMemset(c->gs_var_start, 0, sizeof(int32_t)));
   }
+  const int64_t nids = align4(lay.off[3] + nvar_ids);
+  SEMB_CHECK(nids < (int64_t)2147483647, "semb_set_gather_scatter: id table too long");
+  c->pull_ok = h_info[1] <= 15 && nids < ((int64_t)1 << 28);
+
+  // 3. ids (copies of a segment in ascending local index) and the per-node links of the pull form
+  cudaFree(c->gs_ids);
+  cudaFree(c->gs_link);
+  c->gs_ids = nullptr;
+  c->gs_link = nullptr;
+  SEMB_CUDA(cudaMalloc(&c->gs_ids, sizeof(int32_t) * (size_t)std::max<int64_t>(nids, 4)));
+  SEMB_CUDA(cudaMemset(c->gs_ids, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(nids, 4)));
+  SEMB_CUDA(cudaMalloc(&c->gs_link, sizeof(uint32_t) * (size_t)(n + 2)));
+  SEMB_CUDA(cudaMemset(c->gs_link, 0, sizeof(uint32_t) * (size_t)(n + 2)));
+  if (lay.b[4] > 0) {
+    seg_emit_kernel<<<vec_grid(lay.b[4]), VEC_NT>>>(sorted, d_g2l, d_gst, lay, c->gs_var_start, c->gs_ids, c->gs_link,
+                                                    c->pull_ok ? 1 : 0);
+    SEMB_CUDA(cudaGetLastError());
+  }
+  SEMB_CUDA(cudaDeviceSynchronize());  // tables complete before the context's (non-blocking) stream uses them
+  c->gs_classes.clear();
+  c->gs_classes.push_back(GsClass{2, n2, lay.off[0]});
+  c->gs_classes.push_back(GsClass{4, n4, lay.off[1]});
+  c->gs_classes.push_back(GsClass{8, n8, lay.off[2]});
+  c->gs_var_off = lay.off[3];
+  c->gs_var_nseg = nv;
+  c->gs_nids = nids;
+  c->have_gs = true;
   return build_rmult(c);
 }
 
@@ -710,21 +718,67 @@ int semb_set_mask(semb_ctx* c, const int64_t* mask_ids, int64_t n_mask) {
     SEMB_CHECK(id >= 0 && id < c->n, "semb_set_mask: id out of range");
     bits[id >> 5] |= 1u << (id & 31);
   }
-  cudaFree(c->maskbits);
-  cudaFree(c->mask_ids);
-  c->maskbits = nullptr;
-  c->mask_ids = nullptr;
-  SEMB_CUDA(cudaMalloc(&c->maskbits, sizeof(uint32_t) * words));
-  SEMB_CUDA(cudaMemcpy(c->maskbits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
-  SEMB_CUDA(cudaMalloc(&c->mask_ids, sizeof(int64_t) * std::max<int64_t>(n_mask, 1)));
-  if (n_mask) SEMB_CUDA(cudaMemcpy(c->mask_ids, mask_ids, sizeof(int64_t) * n_mask, cudaMemcpyHostToDevice));
-  SEMB_CUDA(cudaDeviceSynchronize());
-  c->n_mask = n_mask;
+  SEMB_TRY(upload(&c->maskbits, bits.data(), words));
   c->have_mask = true;
-  if (c->vec[4]) {
-    cudaFree(c->vec[4]);
-    c->vec[4] = nullptr;
+  drop_jacobi(c);
+  return 0;
+}
+
+int semb_setup_mask_box(semb_ctx* c, const double* xe, const double* ye, const double* ze, const double* bbox6, double tol,
+                        int mem) {
+  SEMB_CHECK(c && xe && ye && ze && bbox6, "semb_setup_mask_box: NULL argument");
+  SEMB_TRY(bind_device(c));
+  const size_t cnt = (size_t)c->n;
+  DevTmp tx, ty, tz;
+  const double *dx, *dy, *dz;
+  SEMB_TRY(dev_view(xe, mem, cnt, tx, &dx));
+  SEMB_TRY(dev_view(ye, mem, cnt, ty, &dy));
+  SEMB_TRY(dev_view(ze, mem, cnt, tz, &dz));
+  const int64_t words = (c->n + 63) / 64 * 2;
+  cudaFree(c->maskbits);
+  c->maskbits = nullptr;
+  SEMB_CUDA(cudaMalloc(&c->maskbits, sizeof(uint32_t) * (size_t)words));
+  BBox bb;
+  for (int a = 0; a < 3; ++a) {
+    bb.lo[a] = bbox6[2 * a];
+    bb.hi[a] = bbox6[2 * a + 1];
   }
+  mask_bits_kernel<<<vec_grid(words * 32), VEC_NT, 0, c->stream>>>(dx, dy, dz, c->n, bb, tol, c->maskbits, words);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_mask = true;
+  drop_jacobi(c);
+  return 0;
+}
+
+int semb_get_mask(semb_ctx* c, double* mask, int mem) {
+  SEMB_CHECK(c && mask, "semb_get_mask: NULL argument");
+  SEMB_CHECK(c->have_mask, "semb_get_mask: the mask is not set");
+  SEMB_TRY(bind_device(c));
+  Staged v;
+  SEMB_TRY(stage_in(c, mask, mem, c->n, v, false, 0));
+  mask_expand_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->maskbits, v.dev, c->n);
+  SEMB_CUDA(cudaGetLastError());
+  SEMB_TRY(stage_out(c, mask, mem, c->n, v));
+  if (mem == SEMB_DEVICE) SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int semb_minmax(int device, int64_t n, const double* x, double* lo_hi, int mem) {
+  SEMB_CHECK(n > 0 && x && lo_hi, "semb_minmax: bad argument");
+  SEMB_CUDA(cudaSetDevice(device));
+  DevTmp tx, out, tmp;
+  const double* dx;
+  SEMB_TRY(dev_view(x, mem, (size_t)n, tx, &dx));
+  SEMB_TRY(out.alloc(2 * sizeof(double)));
+  size_t tb = 0, tb2 = 0;
+  SEMB_CUDA(cub::DeviceReduce::Min(nullptr, tb, dx, out.as<double>(), (int)n));
+  SEMB_CUDA(cub::DeviceReduce::Max(nullptr, tb2, dx, out.as<double>() + 1, (int)n));
+  tb = std::max(tb, tb2);
+  SEMB_TRY(tmp.alloc(tb));
+  SEMB_CUDA(cub::DeviceReduce::Min(tmp.p, tb, dx, out.as<double>(), (int)n));
+  SEMB_CUDA(cub::DeviceReduce::Max(tmp.p, tb, dx, out.as<double>() + 1, (int)n));
+  SEMB_CUDA(cudaMemcpy(lo_hi, out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -747,10 +801,24 @@ int semb_ax(semb_ctx* c, const double* p, double* ap, int flags, int mem) {
   SEMB_CHECK(mem == SEMB_HOST || p != ap, "semb_ax: in-place application is not supported");
   SEMB_TRY(bind_device(c));
   Staged in, out;
-  SEMB_TRY(stage_in(c, p, mem, c->n, in, true));
-  SEMB_TRY(stage_in(c, ap, mem, c->n, out, false));
-  SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, c->E, nullptr));
-  if (gs) SEMB_TRY(gs_full(c, out.dev, nullptr));
+  SEMB_TRY(stage_in(c, p, mem, c->n, in, true, 0));
+  SEMB_TRY(stage_in(c, ap, mem, c->n, out, false, 1));
+  if (gs && use_pull(c)) {
+    // operator into scratch, then ONE streaming pass that sums the copies of every shared node on the fly
+    SEMB_TRY(ensure_vec(c, 5));
+    double* raw = c->vec[5];
+    SEMB_TRY(launch_ax(c, in.dev, raw, mask, false, 0, 0, c->E, nullptr, nullptr, 0, 0, nullptr));
+    if (c->have_halo) {
+      c->seq_halo++;
+      SEMB_TRY(halo_gather(c, raw, c->stream, nullptr));
+      SEMB_TRY(halo_exchange(c, c->stream));
+    }
+    SEMB_TRY(launch_gs_pull(c, raw, out.dev));
+    if (c->have_halo) SEMB_TRY(halo_scatter(c, out.dev, c->stream, nullptr));
+  } else {
+    SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, 0, c->E, nullptr, nullptr, 0, 0, nullptr));
+    if (gs) SEMB_TRY(gs_full(c, out.dev, nullptr));
+  }
   SEMB_TRY(stage_out(c, ap, mem, c->n, out));
   return 0;
 }
@@ -760,7 +828,7 @@ int semb_gs(semb_ctx* c, double* x, int mem) {
   SEMB_CHECK(c->have_gs, "semb_gs: call semb_set_gather_scatter first");
   SEMB_TRY(bind_device(c));
   Staged v;
-  SEMB_TRY(stage_in(c, x, mem, c->n, v, true));
+  SEMB_TRY(stage_in(c, x, mem, c->n, v, true, 0));
   SEMB_TRY(gs_full(c, v.dev, nullptr));
   SEMB_TRY(stage_out(c, x, mem, c->n, v));
   return 0;
@@ -771,12 +839,10 @@ int semb_mask(semb_ctx* c, double* x, int mem) {
   SEMB_CHECK(c->have_mask, "semb_mask: call semb_set_mask first");
   SEMB_TRY(bind_device(c));
   Staged v;
-  SEMB_TRY(stage_in(c, x, mem, c->n, v, true));
-  if (c->n_mask > 0) {
-    c->launch_count++;
-    mask_kernel<<<vec_grid(c->n_mask), VEC_NT, 0, c->stream>>>(v.dev, c->mask_ids, c->n_mask);
-    SEMB_CUDA(cudaGetLastError());
-  }
+  SEMB_TRY(stage_in(c, x, mem, c->n, v, true, 0));
+  c->launch_count++;
+  mask_apply_bits_kernel<<<vec_grid((c->n + 31) / 32), VEC_NT, 0, c->stream>>>(v.dev, c->maskbits, c->n);
+  SEMB_CUDA(cudaGetLastError());
   SEMB_TRY(stage_out(c, x, mem, c->n, v));
   return 0;
 }
@@ -786,8 +852,9 @@ int semb_dot(semb_ctx* c, const double* x, const double* y, int weighted, double
   SEMB_CHECK(!weighted || c->have_gs, "semb_dot: weighted dot needs semb_set_gather_scatter");
   SEMB_TRY(bind_device(c));
   Staged a, b;
-  SEMB_TRY(stage_in(c, x, mem, c->n, a, true));
-  SEMB_TRY(stage_in(c, y, mem, c->n, b, true));
+  SEMB_TRY(stage_in(c, x, mem, c->n, a, true, 0));
+  if (mem == SEMB_HOST && y == x) b.dev = a.dev;
+  else SEMB_TRY(stage_in(c, y, mem, c->n, b, true, 1));
   const int grid = vec_grid(c->n);
   c->launch_count++;
   if (weighted) dot_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(a.dev, b.dev, c->rmult, c->n, c->partials);
@@ -806,7 +873,7 @@ int semb_diag(semb_ctx* c, double* diag, int mem) {
   SEMB_CHECK(c->have_D && c->have_G, "semb_diag: derivative matrix and geometric factors must be set first");
   SEMB_TRY(bind_device(c));
   Staged v;
-  SEMB_TRY(stage_in(c, diag, mem, c->n, v, false));
+  SEMB_TRY(stage_in(c, diag, mem, c->n, v, false, 0));
   c->launch_count++;
   diag_kernel<<<vec_grid(c->n), VEC_NT, 0, c->stream>>>(c->G6, v.dev, c->E, c->Nq, c->D);
   SEMB_CUDA(cudaGetLastError());
@@ -1010,15 +1077,80 @@ int semb_geom_factors(int device, int Nq, const double* D, const double* w, int6
   return 0;
 }
 
+}  // extern "C"
+
 // ---- solvers ---------------------------------------------------------------
+namespace semb {
+template <int NQ>
+static int launch_fdm_nq(semb_ctx* c, const FdmArgs& a, const LlArgs& ll) {
+  fdm_apply_kernel<NQ><<<(unsigned)c->E, FDM_NT, 0, c->stream>>>(a, ll);
+  SEMB_CUDA(cudaGetLastError());
+  return 0;
+}
+// z = M^-1 r (fdm_kernels.cuh) + sum rmult r z -> s->rdotr_new (+ all-rank sum and scalar step with finish)
+static int launch_fdm(semb_ctx* c, const double* r, double* z, double* hist, int finish, int check_done) {
+  ProfScope ps(c, SEMB_K_DIRECTION);
+  c->launch_count++;
+  FdmArgs a;
+  a.r = r;
+  a.z = z;
+  a.dinv = c->vec[4];
+  a.mult = c->mult;
+  a.S = c->fdm_S;
+  a.esc = c->fdm_invL;
+  a.s = c->scal;
+  a.hist = hist;
+  a.red = GridRed{c->partials, c->partials2, c->ticket};
+  a.ncta = (int)c->E;
+  a.finish = finish;
+  a.check_done = check_done;
+  LlArgs ll = ll_args(c, 0);
+  ll.nranks = 1;
+  if (finish && c->comm != nullptr && c->nranks > 1 && use_p2p(c)) ll = ll_args(c, ++c->seq_scalar);
+  switch (c->Nq) {
+#define SEMB_CASE_F(Q) \
+  case Q:              \
+    return launch_fdm_nq<Q>(c, a, ll);
+    SEMB_CASE_F(2) SEMB_CASE_F(3) SEMB_CASE_F(4) SEMB_CASE_F(5) SEMB_CASE_F(6) SEMB_CASE_F(7) SEMB_CASE_F(8) SEMB_CASE_F(9)
+    SEMB_CASE_F(10) SEMB_CASE_F(11) SEMB_CASE_F(12) SEMB_CASE_F(13) SEMB_CASE_F(14) SEMB_CASE_F(15) SEMB_CASE_F(16)
+#undef SEMB_CASE_F
+    default:
+      break;
+  }
+  set_error("fdm: unsupported Nq");
+  return 2;
+}
+}  // namespace semb
+
+extern "C" {
+
+int semb_set_fdm(semb_ctx* c, const double* S, const double* lambda, const double* elem_scale) {
+  SEMB_CHECK(c && S && lambda && elem_scale, "semb_set_fdm: NULL argument");
+  SEMB_TRY(bind_device(c));
+  const int m = c->Nq - 2;
+  std::vector<double> tab((size_t)std::max(m * m + m, 1), 0.0);
+  for (int q = 0; q < m * m; ++q) tab[q] = S[q];
+  for (int q = 0; q < m; ++q) {
+    SEMB_CHECK(lambda[q] > 0.0, "semb_set_fdm: eigenvalues must be positive");
+    tab[m * m + q] = lambda[q];
+  }
+  SEMB_TRY(upload(&c->fdm_S, tab.data(), tab.size()));
+  SEMB_TRY(upload(&c->fdm_invL, elem_scale, 4 * (size_t)c->E));
+  c->fdm_ready = true;
+  return 0;
+}
+
 int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int precond, int mem, int* niter,
             double* history) {
   SEMB_CHECK(c && b && x && niter, "semb_cg: NULL argument");
   SEMB_CHECK(c->have_D && c->have_G && c->have_gs, "semb_cg: derivative, geometric factors and gather-scatter must be set");
-  SEMB_CHECK(precond == SEMB_PRECOND_NONE || precond == SEMB_PRECOND_JACOBI, "semb_cg: unknown preconditioner");
+  SEMB_CHECK(precond == SEMB_PRECOND_NONE || precond == SEMB_PRECOND_JACOBI || precond == SEMB_PRECOND_FDM,
+             "semb_cg: unknown preconditioner");
+  SEMB_CHECK(precond != SEMB_PRECOND_FDM || c->fdm_ready, "semb_cg: SEMB_PRECOND_FDM without semb_set_fdm");
   SEMB_CHECK(maxit >= 0, "semb_cg: maxit must be non-negative");
+  SEMB_CHECK(mem == SEMB_HOST || (aligned16(b) && aligned16(x)), "semb_cg: device vectors must be 16-byte aligned");
   SEMB_TRY(bind_device(c));
-  const bool jac = precond == SEMB_PRECOND_JACOBI;
+  const bool jac = precond == SEMB_PRECOND_JACOBI, fdm = precond == SEMB_PRECOND_FDM;
   const int64_t n = c->n;
   for (int v = 0; v < 3; ++v) SEMB_TRY(ensure_vec(c, v));
   double *r = c->vec[0], *p = c->vec[1], *Ap = c->vec[2];
@@ -1026,13 +1158,18 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   double* xdev = x;
   if (mem == SEMB_HOST) {
     SEMB_TRY(ensure_vec(c, 3));
-    SEMB_TRY(ensure_vec(c, 5));
-    SEMB_CUDA(cudaMemcpyAsync(c->vec[5], b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    bdev = c->vec[5];
+    Staged sb;
+    SEMB_TRY(stage_in(c, b, mem, n, sb, true, 0));
+    bdev = sb.dev;
     xdev = c->vec[3];
   }
-  if (jac && c->vec[4] == nullptr) SEMB_TRY(build_jacobi(c));
+  if ((jac || fdm) && c->vec[4] == nullptr) SEMB_TRY(build_jacobi(c));
   const double* dinv = c->vec[4];
+  double* z = nullptr;
+  if (fdm) {
+    SEMB_TRY(ensure_vec(c, 5));
+    z = c->vec[5];
+  }
   if (history != nullptr && maxit > 0) {
     if (c->hist_cap < 5 * (int64_t)maxit) {
       cudaFree(c->hist);
@@ -1046,18 +1183,30 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   double* two = reinterpret_cast<double*>(c->scal + 1);
   const int grid = vec_grid(n);
   const bool mask = c->have_mask;
+  const bool multi = c->comm != nullptr && c->nranks > 1;
+  const bool p2p = multi && use_p2p(c);
+  const bool pull = use_pull(c);
 
+  // x = 0, r = b, p = 0; |b|_w^2 and r.z                          (elliptic.py:31-46, iterative.py:48-63)
   c->launch_count += 2;
   if (jac) cg_init_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(bdev, xdev, r, p, c->rmult, dinv, n, c->partials);
   else cg_init_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(bdev, xdev, r, p, c->rmult, nullptr, n, c->partials);
   SEMB_CUDA(cudaGetLastError());
   SEMB_TRY(reduce_partials(c, grid, grid, jac ? 2 : 1, two, nullptr));
   SEMB_TRY(allreduce_sum(c, two, jac ? 2 : 1));
-  cg_init_scalars_kernel<<<1, 1, 0, c->stream>>>(s, two, tol, maxit, jac ? 1 : 0);
+  if (fdm) {
+    SEMB_TRY(launch_fdm(c, r, z, nullptr, 0, 0));
+    SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
+  }
+  cg_init_scalars_kernel<<<1, 1, 0, c->stream>>>(s, two, tol, maxit, jac ? 1 : fdm ? 2 : 0);
   SEMB_CUDA(cudaGetLastError());
 
   const int* done = &s->done;
-  const bool multi = c->comm != nullptr && c->nranks > 1;
+  // direction update folded into the operator's load phase: p = z + beta p with z = r, dinv r, or the FDM output
+  const int dir = jac ? 2 : 1;
+  const double* zsrc = fdm ? z : r;
+  const int64_t nif = c->have_halo ? c->n_if_elems : 0;
+  const int cta1 = ax_num_ctas(c->Nq, 0, nif), cta2 = ax_num_ctas(c->Nq, nif, c->E);
   int issued = 0;
   int chunk = 1;
   while (true) {
@@ -1065,43 +1214,30 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
     c->h_pinned[2] = 0;
     if (c->p2p && c->ll_error)
       SEMB_CUDA(cudaMemcpyAsync(c->h_pinned + 2, c->ll_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    c->h_pinned[3] = 0;
-    if (c->fused_ready && g_ax_fused_gs)
-      SEMB_CUDA(cudaMemcpyAsync(c->h_pinned + 3, c->fz_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SEMB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->h_pinned[2]) {
       set_error("peer-memory exchange timed out: a neighbouring rank did not deliver (rank failure or table mismatch)");
       return 4;
     }
-    if (c->h_pinned[3]) {
-      set_error("fused operator/gather-scatter kernel: a dependency wait timed out (experimental path, ax_fused_gs)");
-      return 5;
-    }
     if (c->h_pinned[1] || issued >= maxit) break;
     const int todo = std::min(chunk, maxit - issued);
     for (int it = 0; it < todo; ++it) {
-      // Ap = mask(A p), local pAp partials      (elliptic.py:48-51)
-      // Ap = dssum(Ap)                          (elliptic.py:54)
-      if (c->have_halo && use_p2p(c)) {
-        // Peer-memory path: one Ax launch; the gather kernel writes this rank's interface sums straight
-        // into the neighbours' memory, the local gather-scatter (80 us) hides the NVLink flight time, the
-        // scatter kernel picks the neighbours' sums up from local memory.  One stream, no NCCL call.
-        const int64_t np = ax_num_partials(c, 0, c->E);
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done, 0));
-        c->seq_scalar++;
-        c->launch_count++;
-        reduce_allreduce_kernel<false><<<1, RED_NT, 0, c->stream>>>(c->partials, np, &s->pAp, s, hist, c->ll_peer_dev,
-                                                                    c->rank, c->nranks, c->seq_scalar, c->ll_error);
-        SEMB_CUDA(cudaGetLastError());
+      // p = z + beta p; Ap = mask(A p); pAp = p.Ap (local copies)         (elliptic.py:70,48-51)
+      // Ap = dssum(Ap)                                                  (elliptic.py:54)
+      if (c->have_halo && p2p) {
+        // Peer-memory path, one stream, no NCCL call: the elements that touch the slab interface first; their
+        // interface sums are written straight into the neighbours' memory (halo_gather) and fly while the
+        // interior elements are computed; the scatter kernel then picks the neighbours' sums up from local
+        // memory and, in a passenger CTA of the same launch, all-reduces pAp.
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, nif, zsrc, dinv, 0, cta1 + cta2, done));
         c->seq_halo++;
         SEMB_TRY(halo_gather(c, Ap, c->stream, done));
-        SEMB_TRY(launch_gs(c, Ap, done));
-        SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done));
+        if (!pull) SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(halo_scatter(c, Ap, c->stream, done, &s->pAp, 1));
       } else if (c->have_halo) {
-        // NCCL path: slab interface first; its partial sums travel to the neighbours while the interior runs
-        const int64_t nif = c->n_if_elems;
-        const int64_t np1 = ax_num_partials(c, 0, nif);
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, nif, done, 0));
+        // NCCL fallback: same order, the exchange on a second stream
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, nif, zsrc, dinv, 0, cta1 + cta2, done));
         SEMB_CUDA(cudaEventRecord(c->ev_if_done, c->stream));
         SEMB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_if_done, 0));
         c->seq_halo++;
@@ -1109,54 +1245,55 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_CUDA(cudaEventRecord(c->ev_gathered, c->comm_stream));
         SEMB_TRY(halo_exchange(c, c->comm_stream));
         SEMB_CUDA(cudaEventRecord(c->ev_exchanged, c->comm_stream));
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, nif, c->E, done, np1));
-        SEMB_TRY(reduce_partials(c, np1 + ax_num_partials(c, nif, c->E), 0, 1, &s->pAp, done));
-        SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
-        SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
-        SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done));
+        if (!pull) {
+          SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
+          SEMB_TRY(launch_gs(c, Ap, done));
+        }
+        // one communicator: its two NCCL operations must not overlap, so the all-reduce follows the exchange
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
+        SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
-      } else if (c->fused_ready && g_ax_fused_gs && mask) {
-        // EXPERIMENTAL: one persistent kernel computes Ap, the local pAp and the gather-scatter
-        SEMB_TRY(launch_ax_fused(c, p, Ap, &s->pAp, done));
-        SEMB_TRY(launch_gs_var_only(c, Ap, done));
       } else {
-        // one GPU: the pAp partials are summed by a passenger CTA of the gather-scatter launch
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, 0, c->E, done));
-        SEMB_TRY(launch_gs(c, Ap, done, c->partials, ax_num_partials(c, 0, c->E), &s->pAp));
+        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, c->E, zsrc, dinv, 0, cta2, done));
+        if (!pull) SEMB_TRY(launch_gs(c, Ap, done));
       }
-      // x, r, rdotr                             (elliptic.py:56-60)
+      // x += alpha p; r -= alpha dssum(Ap); r.z; scalar step              (elliptic.py:56-71)
       {
         ProfScope ps(c, SEMB_K_UPDATE);
         c->launch_count++;
-        // one GPU: the CTA that finishes last sums the partials and does the scalar step (ticket)
-        double* upart = c->partials;
-        unsigned int* ticket = multi ? nullptr : c->ticket;
-        if (jac) cg_update_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, s, n, upart, ticket, hist);
-        else cg_update_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, nullptr, s, n, upart, ticket, hist);
+        // the CTA that finishes last sums the partials, all-reduces them over the ranks (peer memory) and
+        // does the scalar step; with NCCL or FDM that tail runs in separate launches
+        const bool tail = !fdm && (!multi || p2p);
+        unsigned int* ticket = tail ? c->ticket_update : nullptr;
+        LlArgs ll = ll_args(c, 0);
+        ll.nranks = 1;
+        if (tail && p2p) ll = ll_args(c, ++c->seq_scalar);
+#define SEMB_UPDATE(J, P)                                                                                               \
+  cg_update_kernel<J, P><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, c->gs_link, c->gs_ids, s, n, \
+                                                        c->partials, ticket, hist, ll)
+        if (jac && pull) SEMB_UPDATE(true, true);
+        else if (jac) SEMB_UPDATE(true, false);
+        else if (pull) SEMB_UPDATE(false, true);
+        else SEMB_UPDATE(false, false);
+#undef SEMB_UPDATE
         SEMB_CUDA(cudaGetLastError());
       }
-      if (multi && use_p2p(c)) {
-        c->seq_scalar++;
-        c->launch_count++;
-        reduce_allreduce_kernel<true><<<1, RED_NT, 0, c->stream>>>(c->partials, grid, &s->rdotr_new, s, hist,
-                                                                   c->ll_peer_dev, c->rank, c->nranks, c->seq_scalar,
-                                                                   c->ll_error);
-      } else if (c->comm != nullptr && c->nranks > 1) {
+      if (fdm) {
+        // z = M^-1 r, r.z, all-rank sum and scalar step in the same launch (NCCL: separate launches)
+        SEMB_TRY(launch_fdm(c, r, z, hist, (!multi || p2p) ? 1 : 0, 1));
+        if (multi && !p2p) {
+          SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
+          c->launch_count++;
+          cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
+        }
+      } else if (multi && !p2p) {
         SEMB_TRY(reduce_partials(c, grid, 0, 1, &s->rdotr_new, done));
         SEMB_TRY(allreduce_sum(c, &s->rdotr_new, 1));
         c->launch_count++;
         cg_step_scalars_kernel<<<1, 1, 0, c->stream>>>(s, hist);
       }
       SEMB_CUDA(cudaGetLastError());
-      // p = z + beta p                          (elliptic.py:70)
-      {
-        ProfScope ps(c, SEMB_K_DIRECTION);
-        c->launch_count++;
-        if (jac) cg_direction_kernel<true><<<grid, VEC_NT, 0, c->stream>>>(p, r, dinv, s, n);
-        else cg_direction_kernel<false><<<grid, VEC_NT, 0, c->stream>>>(p, r, nullptr, s, n);
-        SEMB_CUDA(cudaGetLastError());
-      }
     }
     issued += todo;
     chunk = std::min(chunk * 2, 16);
@@ -1255,6 +1392,7 @@ int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_a
   return 0;
 }
 
+
 // ---- multi-GPU -------------------------------------------------------------
 int semb_comm_unique_id(char* id128) {
   SEMB_CHECK(id128 != nullptr, "semb_comm_unique_id: NULL argument");
@@ -1287,6 +1425,7 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
   SEMB_CHECK(c != nullptr && nneigh >= 0 && n_if >= 0, "semb_set_halo: bad argument");
   SEMB_CHECK(c->have_gs, "semb_set_halo: call semb_set_gather_scatter first");
   SEMB_CHECK(nneigh == 0 || c->comm != nullptr, "semb_set_halo: call semb_comm_init first");
+  SEMB_CHECK(nneigh <= LL_MAXR, "semb_set_halo: too many neighbours");
   SEMB_CHECK(n_if_elems >= 0 && n_if_elems <= c->E, "semb_set_halo: n_if_elems out of range");
   SEMB_TRY(bind_device(c));
   c->nb_rank.assign(nb_rank, nb_rank + nneigh);
@@ -1301,6 +1440,10 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
   c->n_if_elems = n_if_elems;
   if (c->n_send > 0) {
     SEMB_CHECK(send_start && send_ids && src_start && src_off && copy_start && copy_ids, "semb_set_halo: NULL table");
+    for (int64_t q = 0; q < send_start[c->n_send]; ++q)
+      SEMB_CHECK(send_ids[q] >= 0 && send_ids[q] < c->n, "semb_set_halo: send id out of range");
+    for (int64_t q = 0; q < copy_start[n_if]; ++q)
+      SEMB_CHECK(copy_ids[q] >= 0 && copy_ids[q] < c->n, "semb_set_halo: copy id out of range");
     SEMB_TRY(upload(&c->send_start, send_start, (size_t)c->n_send + 1));
     SEMB_TRY(upload(&c->send_ids, send_ids, (size_t)send_start[c->n_send]));
     SEMB_TRY(upload(&c->src_start, src_start, (size_t)n_if + 1));
@@ -1310,10 +1453,25 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
     cudaFree(c->hbuf);
     c->hbuf = nullptr;
     SEMB_CUDA(cudaMalloc(&c->hbuf, sizeof(double) * 2 * (size_t)c->n_send));
+    // the halo kernels complete the interface nodes: take them out of the pull form of the local schedule
+    if (c->gs_link != nullptr) {
+      clear_links_kernel<<<vec_grid(copy_start[n_if]), VEC_NT, 0, c->stream>>>(c->gs_link, c->copy_ids, copy_start[n_if]);
+      SEMB_CUDA(cudaGetLastError());
+      SEMB_CUDA(cudaStreamSynchronize(c->stream));
+    }
   }
   c->have_halo = c->nranks > 1;
-  if (c->n_send > c->ll_halo_cap) c->p2p = false;  // receive region too small for the new tables: back to NCCL until re-attached
+  // New tables invalidate the peer-memory layout on EVERY rank (a collective decision: a per-rank
+  // fallback would leave one side on NCCL while the other spins on peer words): NCCL until all ranks
+  // have gone through semb_p2p_alloc / semb_p2p_attach again.
+  c->p2p = false;
   return build_rmult(c);  // multiplicities now count the copies on the other ranks too
+}
+
+static void close_peer_mappings(semb_ctx* c) {
+  for (int r = 0; r < (int)c->ll_peer.size(); ++r)
+    if (r != c->rank && c->ll_peer[r]) cudaIpcCloseMemHandle(c->ll_peer[r]);
+  c->ll_peer.clear();
 }
 
 int semb_p2p_alloc(semb_ctx* c, int64_t halo_capacity, char* handle64) {
@@ -1323,18 +1481,21 @@ int semb_p2p_alloc(semb_ctx* c, int64_t halo_capacity, char* handle64) {
   SEMB_CHECK(c->nranks <= LL_MAXR, "semb_p2p_alloc: more ranks than the peer-memory path supports");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   SEMB_TRY(bind_device(c));
-  // the same capacity on every rank: writers compute the parity offset inside the READER's region
+  SEMB_CUDA(cudaStreamSynchronize(c->stream));
+  c->p2p = false;
+  // Every (re-)attachment starts from a fresh, zeroed region and a fresh handle: the capacity fixes the
+  // parity offsets that the WRITERS compute inside this region, and stale sequence numbers of an earlier
+  // layout must not be mistaken for data.  Old mappings of the peers' regions are closed first.
+  close_peer_mappings(c);
+  cudaFree(c->ll_local);
+  c->ll_local = nullptr;
   c->ll_halo_cap = std::max<int64_t>(halo_capacity, 1);
-  if (c->ll_error == nullptr) {
-    SEMB_CUDA(cudaMalloc(&c->ll_error, sizeof(int)));
-    SEMB_CUDA(cudaMemset(c->ll_error, 0, sizeof(int)));
-  }
+  if (c->ll_error == nullptr) SEMB_CUDA(cudaMalloc(&c->ll_error, sizeof(int)));
+  SEMB_CUDA(cudaMemset(c->ll_error, 0, sizeof(int)));
   const size_t words = (size_t)LL_SCALAR_WORDS + 2 * 2 * (size_t)c->ll_halo_cap;
-  if (c->ll_local == nullptr) {
-    SEMB_CUDA(cudaMalloc(&c->ll_local, words * sizeof(unsigned long long)));
-    SEMB_CUDA(cudaMemset(c->ll_local, 0, words * sizeof(unsigned long long)));
-    SEMB_CUDA(cudaDeviceSynchronize());
-  }
+  SEMB_CUDA(cudaMalloc(&c->ll_local, words * sizeof(unsigned long long)));
+  SEMB_CUDA(cudaMemset(c->ll_local, 0, words * sizeof(unsigned long long)));
+  SEMB_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   SEMB_CUDA(cudaIpcGetMemHandle(&h, c->ll_local));
   std::memcpy(handle64, &h, sizeof(h));
@@ -1345,6 +1506,7 @@ int semb_p2p_attach(semb_ctx* c, const char* handles, const int64_t* peer_recv_o
   SEMB_CHECK(c && handles && (peer_recv_off || c->nb_rank.empty()), "semb_p2p_attach: NULL argument");
   SEMB_CHECK(c->ll_local != nullptr, "semb_p2p_attach: call semb_p2p_alloc first");
   SEMB_TRY(bind_device(c));
+  close_peer_mappings(c);
   c->ll_peer.assign(c->nranks, nullptr);
   for (int r = 0; r < c->nranks; ++r) {
     if (r == c->rank) {
@@ -1359,34 +1521,13 @@ int semb_p2p_attach(semb_ctx* c, const char* handles, const int64_t* peer_recv_o
   }
   SEMB_TRY(upload(&c->ll_peer_dev, c->ll_peer.data(), c->ll_peer.size()));
   std::vector<int64_t> po(peer_recv_off, peer_recv_off + c->nb_rank.size());
+  for (size_t q = 0; q < po.size(); ++q)
+    SEMB_CHECK(po[q] >= 0 && po[q] + (c->nb_off[q + 1] - c->nb_off[q]) <= c->ll_halo_cap,
+               "semb_p2p_attach: a block does not fit the neighbour's receive region");
   c->halo_peers = make_halo_peers(c, po);
   c->seq_scalar = 0;
   c->seq_halo = 0;
   c->p2p = true;
-  return 0;
-}
-
-// Host-only: closure tables of the experimental fused kernel, for unit tests (no device needed).
-// Call with out pointers NULL to get the sizes: sizes[0] = len(ids), sizes[1] = len(dep_elem), sizes[2] =
-// segments of other lengths.  Arrays: base, dep_start int32[E+1]; n2, n4, n8 uint16[E].
-int semb_host_closure_tables(int64_t E, int64_t Np, const int64_t* g2l, const int64_t* gstart, int64_t nglobal,
-                             int64_t* sizes, int32_t* base, uint16_t* n2, uint16_t* n4, uint16_t* n8, int32_t* ids,
-                             int32_t* dep_start, int32_t* dep_elem) {
-  SEMB_CHECK(sizes != nullptr, "semb_host_closure_tables: sizes is NULL");
-  ClosureTables t;
-  const int rc = build_closure_tables(E, Np, g2l, gstart, nglobal, t);
-  SEMB_CHECK(rc == 0, "semb_host_closure_tables: bad input or too many segments per element");
-  sizes[0] = (int64_t)t.ids.size();
-  sizes[1] = (int64_t)t.dep_elem.size();
-  sizes[2] = t.other_segments;
-  if (base == nullptr) return 0;
-  std::memcpy(base, t.base.data(), sizeof(int32_t) * t.base.size());
-  std::memcpy(dep_start, t.dep_start.data(), sizeof(int32_t) * t.dep_start.size());
-  std::memcpy(n2, t.n2.data(), sizeof(uint16_t) * t.n2.size());
-  std::memcpy(n4, t.n4.data(), sizeof(uint16_t) * t.n4.size());
-  std::memcpy(n8, t.n8.data(), sizeof(uint16_t) * t.n8.size());
-  if (!t.ids.empty()) std::memcpy(ids, t.ids.data(), sizeof(int32_t) * t.ids.size());
-  if (!t.dep_elem.empty()) std::memcpy(dep_elem, t.dep_elem.data(), sizeof(int32_t) * t.dep_elem.size());
   return 0;
 }
 
@@ -1457,16 +1598,8 @@ int semb_set_tuning(const char* name, int value) {
     g_ax_l2_prefetch = value;
     return 0;
   }
-  if (std::strcmp(name, "ax_tuned_high_order") == 0) {
-    g_ax_tuned_high_order = value;
-    return 0;
-  }
-  if (std::strcmp(name, "ax_fused_gs") == 0) {
-    g_ax_fused_gs = value;
-    return 0;
-  }
-  if (std::strcmp(name, "ax_fused_lag") == 0) {
-    g_ax_fused_lag = value;
+  if (std::strcmp(name, "gs_pull") == 0) {
+    g_gs_pull = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {

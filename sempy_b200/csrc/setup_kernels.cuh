@@ -97,4 +97,141 @@ __global__ void geom_factors_kernel(const double* __restrict__ xe, const double*
   }
 }
 
+// ---------------------------------------------------------------------------
+// Gather-scatter schedule on the device, from the numbering arrays (global_to_local, global_start) of
+// sempy/mesh.py:422-423.  Only segments with more than one local copy are kept, grouped by length
+// (2 | 4 | 8 | anything else) and ordered by their lowest local index inside a group, the copies of a
+// segment in ascending local index (the fixed summation order of both the push and the pull kernels).
+// ---------------------------------------------------------------------------
+constexpr unsigned long long SEG_CLASS_SHIFT = 40;
+
+// key = (class << 40) | lowest local index; class 4 = single-copy segment (sorted to the end, dropped)
+__global__ void seg_keys_kernel(const int64_t* __restrict__ g2l, const int64_t* __restrict__ gstart, int64_t nseg, int64_t n,
+                                unsigned long long* __restrict__ keys, int32_t* __restrict__ vals, int* __restrict__ info) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lo = gstart[s], len = gstart[s + 1] - lo;
+    unsigned long long cls = 4, first = 0;
+    if (len < 1 || lo < 0 || lo + len > n) {
+      atomicOr(info + 0, 1);  // malformed offsets
+    } else {
+      int64_t mn = n;
+      bool bad = false;
+      for (int64_t q = lo; q < lo + len; ++q) {
+        const int64_t id = g2l[q];
+        bad |= id < 0 || id >= n;
+        mn = id < mn ? id : mn;
+      }
+      if (bad) {
+        atomicOr(info + 0, 2);  // local index out of range
+        mn = 0;
+      }
+      if (len > 1) {
+        cls = len == 2 ? 0 : len == 4 ? 1 : len == 8 ? 2 : 3;
+        first = (unsigned long long)mn;
+        if (len > 15) atomicMax(info + 1, (int)(len > 0x7fffffff ? 0x7fffffff : len));
+      }
+    }
+    keys[s] = (cls << SEG_CLASS_SHIFT) | first;
+    vals[s] = (int32_t)s;
+  }
+}
+
+// bounds[c] = first sorted position whose class is >= c (c = 0..4); bounds[4] = number of shared segments
+__global__ void seg_bounds_kernel(const unsigned long long* __restrict__ keys, int64_t nseg, int64_t* __restrict__ bounds) {
+  const int c = threadIdx.x;
+  if (c > 4) return;
+  const unsigned long long target = (unsigned long long)c << SEG_CLASS_SHIFT;
+  int64_t lo = 0, hi = nseg;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1;
+    else hi = mid;
+  }
+  bounds[c] = lo;
+}
+
+// lengths of the irregular segments (sorted positions [b3, b4)) for the CSR offsets
+__global__ void seg_var_len_kernel(const int32_t* __restrict__ vals, const int64_t* __restrict__ gstart, int64_t b3, int64_t b4,
+                                   int32_t* __restrict__ len_out) {
+  for (int64_t t = b3 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < b4; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = vals[t];
+    len_out[t - b3] = (int32_t)(gstart[s + 1] - gstart[s]);
+  }
+}
+
+struct SegLayout {
+  int64_t b[5];     // class boundaries in the sorted order
+  int64_t off[4];   // start of each class in ids (multiples of 4 ints)
+};
+
+// writes the ids of every shared segment (ascending) and the link of each of its copies
+__global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t* __restrict__ g2l,
+                                const int64_t* __restrict__ gstart, const SegLayout lay, const int32_t* __restrict__ var_start,
+                                int32_t* __restrict__ ids, uint32_t* __restrict__ link, int link_ok) {
+  const int64_t total = lay.b[4];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = vals[t];
+    const int64_t lo = gstart[s];
+    const int len = (int)(gstart[s + 1] - lo);
+    const int cls = t < lay.b[1] ? 0 : t < lay.b[2] ? 1 : t < lay.b[3] ? 2 : 3;
+    const int64_t dst = cls < 3 ? lay.off[cls] + (t - lay.b[cls]) * len : lay.off[3] + var_start[t - lay.b[3]];
+    int32_t* out = ids + dst;
+    // insertion sort straight into the output (segments are short)
+    for (int c = 0; c < len; ++c) {
+      const int32_t id = (int32_t)g2l[lo + c];
+      int pos = c;
+      while (pos > 0 && out[pos - 1] > id) {
+        out[pos] = out[pos - 1];
+        --pos;
+      }
+      out[pos] = id;
+    }
+    if (link_ok && len <= 15) {
+      const uint32_t lk = ((uint32_t)len << 28) | (uint32_t)dst;
+      for (int c = 0; c < len; ++c) link[out[c]] = lk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Dirichlet mask of the bounding box on the device (Mesh.setup_mask, sempy/mesh.py:449-477): bit = 1 where
+// any coordinate is within tol of the box (the reference's mask is 0 there).
+// ---------------------------------------------------------------------------
+struct BBox {
+  double lo[3], hi[3];
+};
+__global__ void mask_bits_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                 int64_t n, const BBox bb, double tol, uint32_t* __restrict__ bits, int64_t nwords) {
+  // one thread per node, one warp per 32-bit word
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nwords * 32; q += stride) {
+    bool m = false;
+    if (q < n) {
+      const double cx = x[q], cy = y[q], cz = z[q];
+      m = fabs(cx - bb.lo[0]) < tol || fabs(cx - bb.hi[0]) < tol || fabs(cy - bb.lo[1]) < tol || fabs(cy - bb.hi[1]) < tol ||
+          fabs(cz - bb.lo[2]) < tol || fabs(cz - bb.hi[2]) < tol;
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) bits[q >> 5] = w;
+  }
+}
+// x[q] = 0 where bit q is set   (Mesh.apply_mask, sempy/mesh.py:487-494)
+__global__ void mask_apply_bits_kernel(double* __restrict__ x, const uint32_t* __restrict__ bits, int64_t n) {
+  const int64_t nwords = (n + 31) >> 5;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t b = bits[w];
+    while (b) {
+      const int k = __ffs(b) - 1;
+      b &= b - 1;
+      const int64_t q = w * 32 + k;
+      if (q < n) x[q] = 0.0;
+    }
+  }
+}
+// mask as the reference stores it: 0.0 at Dirichlet nodes, 1.0 elsewhere
+__global__ void mask_expand_kernel(const uint32_t* __restrict__ bits, double* __restrict__ mask, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    mask[q] = ((bits[q >> 5] >> (q & 31)) & 1u) ? 0.0 : 1.0;
+}
+
 }  // namespace semb

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace semb {
 
@@ -75,33 +76,13 @@ struct GsPlan {
   int64_t n2, n4, n8;        // segments per class
   int64_t off2, off4, off8;  // start of each class in ids (multiples of 4 ints)
   int b2, b4, b8;            // blocks per class
-  // optional passenger: one more CTA (the last one) sums red_n per-CTA partials into *red_out while the
-  // gather-scatter runs -- in semb_cg this is the pAp reduction, which only the update kernel AFTER the
-  // gather-scatter needs, so it costs neither a launch nor time on the critical path
-  const double* red_src;
-  int64_t red_n;
-  double* red_out;
 };
-
-__device__ __forceinline__ double block_sum(double v);
 
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
                 const int* __restrict__ done) {
   if (done != nullptr && *done) return;
   int b = blockIdx.x;
-  if (b == plan.b2 + plan.b4 + plan.b8) {  // the passenger CTA (only launched when red_out is set)
-    double v0 = 0.0, v1 = 0.0;
-    int64_t t = threadIdx.x;
-    for (; t + VEC_NT < plan.red_n; t += 2 * VEC_NT) {
-      v0 += plan.red_src[t];
-      v1 += plan.red_src[t + VEC_NT];
-    }
-    for (; t < plan.red_n; t += VEC_NT) v0 += plan.red_src[t];
-    const double s = block_sum(v0 + v1);
-    if (threadIdx.x == 0) *plan.red_out = s;
-    return;
-  }
   if (b < plan.b2) {
     const int64_t stride = (int64_t)plan.b2 * VEC_NT;
     for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += 4 * stride)
@@ -132,6 +113,86 @@ gs_var_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const int
     for (int q = lo; q < hi; ++q) sum += x[ids[q]];
     for (int q = lo; q < hi; ++q) x[ids[q]] = sum;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Pull form of the same schedule.  link[q] = (len << 28) | offset of node q's segment in `ids` (0: the node
+// has no other local copy, or the halo kernels complete it).  The consumer of a gather-scattered vector
+// reads, for every shared node, the copies of its segment in ascending local index and adds them in that
+// order -- every copy computes the bitwise identical sum, nothing is written back, and the separate pass
+// over the vector (K2: 18 B of sector traffic per node at 48 % of the DRAM peak, profiles/r01_summary.md)
+// disappears.  Inside semb_cg the consumer is the update kernel (r -= alpha * dssum(Ap)), for
+// semb_ax(GS) an out-of-place streaming kernel.  The gathers hit L2: the copies of a node sit in
+// elements that are neighbours in the mesh, and every sector gathered is also read by the stream itself.
+// ---------------------------------------------------------------------------
+constexpr uint32_t GS_LINK_OFF_MASK = 0x0fffffffu;
+
+__device__ __forceinline__ double gs_pull(const double* __restrict__ v, const int32_t* __restrict__ ids, uint32_t link,
+                                          int64_t q, double own) {
+  const int len = (int)(link >> 28);
+  const int32_t* p = ids + (link & GS_LINK_OFF_MASK);
+  if (len == 2) {
+    const int2 i2 = __ldg(reinterpret_cast<const int2*>(p));
+    const double a = i2.x == q ? own : v[i2.x];
+    const double b = i2.y == q ? own : v[i2.y];
+    return a + b;
+  }
+  if (len == 4) {
+    const int4 i4 = __ldg(reinterpret_cast<const int4*>(p));
+    const double a = i4.x == q ? own : v[i4.x];
+    const double b = i4.y == q ? own : v[i4.y];
+    const double c = i4.z == q ? own : v[i4.z];
+    const double d = i4.w == q ? own : v[i4.w];
+    return ((a + b) + c) + d;
+  }
+  if (len == 8) {
+    const int4 i4 = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 j4 = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    const double a = i4.x == q ? own : v[i4.x];
+    const double b = i4.y == q ? own : v[i4.y];
+    const double c = i4.z == q ? own : v[i4.z];
+    const double d = i4.w == q ? own : v[i4.w];
+    const double e = j4.x == q ? own : v[j4.x];
+    const double f = j4.y == q ? own : v[j4.y];
+    const double g = j4.z == q ? own : v[j4.z];
+    const double h = j4.w == q ? own : v[j4.w];
+    return ((((((a + b) + c) + d) + e) + f) + g) + h;
+  }
+  const int first = __ldg(p);
+  double s = first == q ? own : v[first];
+  for (int c = 1; c < len; ++c) {
+    const int id = __ldg(p + c);
+    s += id == q ? own : v[id];
+  }
+  return s;
+}
+
+// out = dssum(in), out of place (in != out), streaming.
+__global__ void __launch_bounds__(VEC_NT)
+gs_pull_kernel(const double* __restrict__ in, double* __restrict__ out, const uint32_t* __restrict__ link,
+               const int32_t* __restrict__ ids, int64_t n) {
+  const int64_t n2 = n >> 1;
+  const double2* in2 = reinterpret_cast<const double2*>(in);
+  const uint2* l2 = reinterpret_cast<const uint2*>(link);
+  double2* o2 = reinterpret_cast<double2*>(out);
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
+    double2 v = in2[q];
+    const uint2 lk = __ldg(l2 + q);
+    if (lk.x) v.x = gs_pull(in, ids, lk.x, 2 * q, v.x);
+    if (lk.y) v.y = gs_pull(in, ids, lk.y, 2 * q + 1, v.y);
+    o2[q] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t q = n - 1;
+    const uint32_t lk = link[q];
+    out[q] = lk ? gs_pull(in, ids, lk, q, in[q]) : in[q];
+  }
+}
+
+// link[copy] = 0 for the copies of interface nodes (their sum is completed by the halo kernels)
+__global__ void clear_links_kernel(uint32_t* __restrict__ link, const int32_t* __restrict__ copy_ids, int64_t ncopy) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < ncopy; q += (int64_t)gridDim.x * blockDim.x)
+    link[copy_ids[q]] = 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -259,16 +320,36 @@ halo_gather_p2p_kernel(const double* __restrict__ x, const int64_t* __restrict__
   }
 }
 
+// Arguments of the in-kernel all-rank sum (peer memory); nranks <= 1 switches it off.
+struct LlArgs {
+  unsigned long long* const* peers;
+  int rank, nranks;
+  unsigned int seq;
+  int* ll_error;
+};
+
 // halo_scatter reading the neighbours' partial sums from this rank's own LL region (spins until they
-// have arrived); same ascending-rank summation order as the NCCL form.
+// have arrived); same ascending-rank summation order as the NCCL form.  With pass_vals != nullptr the
+// launch carries one more CTA (the last) that all-reduces pass_count scalars in place while the others
+// wait for their halo words: inside semb_cg that is the pAp sum, so the two exchanges of the operator
+// phase share one launch and overlap.
 __global__ void __launch_bounds__(VEC_NT)
 halo_scatter_p2p_kernel(double* __restrict__ x, const double* __restrict__ hbuf, const unsigned long long* __restrict__ ll_halo,
                         int64_t n_send, const int64_t* __restrict__ src_start, const int32_t* __restrict__ src_off,
                         const int64_t* __restrict__ copy_start, const int32_t* __restrict__ copy_ids, int64_t n_if,
-                        int64_t halo_cap, unsigned int seq, const int* __restrict__ done, int* ll_error) {
+                        int64_t halo_cap, unsigned int seq, const int* __restrict__ done, int* ll_error,
+                        double* pass_vals, int pass_count, const LlArgs pass) {
   if (done != nullptr && *done) return;
+  int nblk = gridDim.x;
+  if (pass_vals != nullptr) {
+    nblk -= 1;
+    if ((int)blockIdx.x == nblk) {
+      ll_allreduce_cta(pass_vals, pass_count, pass.peers, pass.rank, pass.nranks, pass.seq, pass.ll_error);
+      return;
+    }
+  }
   const unsigned long long* base = ll_halo + (int64_t)(seq & 1) * halo_cap * 2;
-  for (int64_t i = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; i < n_if; i += (int64_t)gridDim.x * VEC_NT) {
+  for (int64_t i = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; i < n_if; i += (int64_t)nblk * VEC_NT) {
     double s = 0.0;
     for (int64_t q = src_start[i]; q < src_start[i + 1]; ++q) {
       const int64_t off = src_off[q];
@@ -351,8 +432,8 @@ dot_kernel(const double* __restrict__ x, const double* __restrict__ y, const dou
 }
 
 // ---------------------------------------------------------------------------
-// CG set-up:  x = 0, r = b, p = z = Minv r;  partial sums of |b|_w^2 and r.z
-// (sempy/elliptic.py:31-46; sempy/iterative.py:48-63 for the PCG form).
+// CG set-up:  x = 0, r = b, p = 0 (the first operator launch forms p = z + 0 * p with z = Minv r);
+// partial sums of |b|_w^2 and r.z  (sempy/elliptic.py:31-46; sempy/iterative.py:48-63 for the PCG form).
 // ---------------------------------------------------------------------------
 template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_NT)
@@ -364,14 +445,10 @@ cg_init_kernel(const double* __restrict__ b, double* __restrict__ x, double* __r
     const double bq = b[q];
     const double wb = rmult[q] * bq;
     nb = fma(wb, bq, nb);
-    double z = bq;
-    if (JACOBI) {
-      z = dinv[q] * bq;
-      rz = fma(wb, z, rz);
-    }
+    if (JACOBI) rz = fma(wb, dinv[q] * bq, rz);
     x[q] = 0.0;
     r[q] = bq;
-    p[q] = z;
+    p[q] = 0.0;
   }
   const double s0 = block_sum(nb);
   if (threadIdx.x == 0) partials[blockIdx.x] = s0;
@@ -382,10 +459,11 @@ cg_init_kernel(const double* __restrict__ b, double* __restrict__ x, double* __r
   }
 }
 
-// two[0] = |b|_w^2, two[1] = r.z (Jacobi only)
-__global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double tol, int maxit, int jacobi) {
+// two[0] = |b|_w^2, two[1] = r.z (precond 1 = Jacobi); precond 2 (FDM): r.z is already in s->rdotr_new
+__global__ void cg_init_scalars_kernel(CgScalars* s, const double* two, double tol, int maxit, int precond) {
+  const int jacobi = precond != 0;
   const double norm_b = two[0];
-  const double rdotr = jacobi ? two[1] : norm_b;
+  const double rdotr = precond == 2 ? s->rdotr_new : precond == 1 ? two[1] : norm_b;
   s->norm_b = norm_b;
   s->TOL = fmax(tol * tol * norm_b, tol * tol);
   s->rdotr = rdotr;
@@ -421,11 +499,12 @@ __device__ __forceinline__ void cg_step_scalars(CgScalars* s, double* hist) {
   s->done = !(s->niter < s->maxit && r1 > s->TOL) ? 1 : 0;
 }
 
-// Single GPU: the CTA that finishes last adds the per-CTA partials (fixed order -> repeatable whichever
-// CTA it is) and performs the scalar step, so no separate reduction launch sits between the update and
-// the direction kernel.  ticket == nullptr (several GPUs) leaves that to reduce_allreduce_kernel.
+// The CTA that finishes last adds the per-CTA partials (fixed order -> repeatable whichever CTA it is),
+// sums over the ranks when there are several (peer-memory all-reduce inside this CTA) and performs the
+// scalar step, so no reduction launch follows the update.  ticket == nullptr (NCCL fallback) leaves
+// all of that to separate launches.
 __device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* partials, unsigned int* ticket,
-                                                 double* hist) {
+                                                 double* hist, const LlArgs& ll) {
   if (ticket == nullptr) return;
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
@@ -440,25 +519,33 @@ __device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* par
   const double tot = block_sum(v);
   if (threadIdx.x == 0) {
     s->rdotr_new = tot;
-    cg_step_scalars(s, hist);
     *ticket = 0;
   }
+  if (ll.nranks > 1) {
+    __syncthreads();
+    ll_allreduce_cta(&s->rdotr_new, 1, ll.peers, ll.rank, ll.nranks, ll.seq, ll.ll_error);
+  }
+  if (threadIdx.x == 0) cg_step_scalars(s, hist);
 }
 
 // ---------------------------------------------------------------------------
-// K3: x += alpha p ; r -= alpha Ap ; partial of sum rmult r r (or rmult r dinv r)
-// (sempy/elliptic.py:52-60; iterative.py:66-73).  56 B per node (+8 Jacobi).
+// K3: x += alpha p ; r -= alpha dssum(Ap) ; partial of sum rmult r r (or rmult r dinv r)
+// (sempy/elliptic.py:52-60; iterative.py:66-73).  With PULL the gather-scatter of Ap (elliptic.py:54)
+// happens here: Ap holds the UNSUMMED operator output and every shared node adds the copies of its
+// segment on the fly (gs_pull), so Ap is neither re-read by a separate pass nor written back.
+// 57 B per node with Jacobi (+4 link, +~2.3 ids with PULL).
 // ---------------------------------------------------------------------------
 // The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node) and
 // turned back into the identical double through a small shared-memory table of 1.0/c (a division in
 // the loop costs a MUFU + Newton sequence with a slow-path call per element and made the kernel
 // 16 % slower than reading the 8-byte weights).
-template <bool JACOBI>
+template <bool JACOBI, bool PULL>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                  const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
-                 CgScalars* __restrict__ s, int64_t n, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                 double* __restrict__ hist) {
+                 const uint32_t* __restrict__ link, const int32_t* __restrict__ ids, CgScalars* __restrict__ s, int64_t n,
+                 double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ hist,
+                 const LlArgs ll) {
   if (s->done) return;
   __shared__ double s_rcp[256];
   s_rcp[threadIdx.x] = 1.0 / (double)(threadIdx.x > 0 ? threadIdx.x : 1);  // VEC_NT == 256 entries
@@ -472,8 +559,15 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   const double2* a2 = reinterpret_cast<const double2*>(Ap);
   const uchar2* m2 = reinterpret_cast<const uchar2*>(mult);
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  const uint2* l2 = reinterpret_cast<const uint2*>(link);
   for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    const double2 pv = p2[q], av = a2[q];
+    const double2 pv = p2[q];
+    double2 av = a2[q];
+    if (PULL) {
+      const uint2 lk = __ldg(l2 + q);
+      if (lk.x) av.x = gs_pull(Ap, ids, lk.x, 2 * q, av.x);
+      if (lk.y) av.y = gs_pull(Ap, ids, lk.y, 2 * q + 1, av.y);
+    }
     const uchar2 mc = m2[q];
     double2 xv = x2[q], rv = r2[q];
     xv.x = xv.x + alpha * pv.x;
@@ -494,81 +588,22 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t q = n - 1;
+    double av = Ap[q];
+    if (PULL && link[q]) av = gs_pull(Ap, ids, link[q], q, av);
     const double xv = x[q] + alpha * p[q];
-    const double rv = r[q] - alpha * Ap[q];
+    const double rv = r[q] - alpha * av;
     x[q] = xv;
     r[q] = rv;
     acc = fma(s_rcp[mult[q]] * rv, JACOBI ? dinv[q] * rv : rv, acc);
   }
   const double sum = block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = sum;
-  cg_update_finish(s, partials, ticket, hist);
+  cg_update_finish(s, partials, ticket, hist, ll);
 }
 
 __global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
   if (s->done) return;
   cg_step_scalars(s, hist);
-}
-// Several GPUs: per-CTA partials -> rank sum -> all-rank sum (peer memory) in ONE launch, optionally
-// followed by the scalar step.  `done` is not consulted for the all-reduce itself: every rank must
-// take part in every exchange.
-template <bool STEP>
-__global__ void __launch_bounds__(RED_NT)
-reduce_allreduce_kernel(const double* __restrict__ partials, int64_t n, double* out, CgScalars* s, double* hist,
-                        unsigned long long* const* __restrict__ peers, int rank, int nranks, unsigned int seq,
-                        int* ll_error) {
-  __shared__ double s_red[RED_NT / 32];
-  double v0 = 0.0, v1 = 0.0;
-  int64_t t = threadIdx.x;
-  for (; t + RED_NT < n; t += 2 * RED_NT) {
-    v0 += partials[t];
-    v1 += partials[t + RED_NT];
-  }
-  for (; t < n; t += RED_NT) v0 += partials[t];
-  double v = v0 + v1;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double w = s_red[threadIdx.x];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if (threadIdx.x == 0) *out = w;
-  }
-  __syncthreads();
-  ll_allreduce_cta(out, 1, peers, rank, nranks, seq, ll_error);
-  if (STEP && threadIdx.x == 0 && !s->done) cg_step_scalars(s, hist);
-}
-
-// K4: p = z + beta p with z = r or dinv r (sempy/elliptic.py:70; iterative.py:83). 24 B per node.
-template <bool JACOBI>
-__global__ void __launch_bounds__(VEC_NT)
-cg_direction_kernel(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ dinv,
-                    const CgScalars* __restrict__ s, int64_t n) {
-  if (s->done) return;
-  const double beta = s->beta;
-  const int64_t n2 = n >> 1;
-  double2* p2 = reinterpret_cast<double2*>(p);
-  const double2* r2 = reinterpret_cast<const double2*>(r);
-  const double2* d2 = reinterpret_cast<const double2*>(dinv);
-  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    double2 pv = p2[q];
-    double2 zv = r2[q];
-    if (JACOBI) {
-      const double2 dv = d2[q];
-      zv.x *= dv.x;
-      zv.y *= dv.y;
-    }
-    pv.x = zv.x + beta * pv.x;
-    pv.y = zv.y + beta * pv.y;
-    p2[q] = pv;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int64_t q = n - 1;
-    const double z = JACOBI ? dinv[q] * r[q] : r[q];
-    p[q] = z + beta * p[q];
-  }
 }
 
 // dinv = mask ? 0 : 1/diag   (Jacobi preconditioner on assembled diagonal)
@@ -583,9 +618,11 @@ __global__ void jacobi_invert_kernel(double* __restrict__ d, const uint32_t* __r
 __global__ void fill_kernel(double* __restrict__ x, double v, int64_t n) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) x[q] = v;
 }
-__global__ void reciprocal_kernel(double* __restrict__ x, unsigned char* __restrict__ count, int64_t n) {
+// info[0] is raised when a node has more than 255 copies (the update kernel's weights are one byte)
+__global__ void reciprocal_kernel(double* __restrict__ x, unsigned char* __restrict__ count, int64_t n, int* __restrict__ info) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const double c = x[q];  // exact small integer: sum of ones
+    if (c > 255.0) atomicOr(info, 1);
     count[q] = (unsigned char)(c < 255.0 ? c : 255.0);
     x[q] = 1.0 / c;
   }

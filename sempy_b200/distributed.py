@@ -110,12 +110,15 @@ def interface_first_order(local_hexes, shared_vertex):
     return order, int(touches.sum())
 
 
-def build_halo(comm, xe, ye, ze, cand, global_id, g2l, gstart, numbering):
+def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     """Interface tables of this rank (arguments of semb_set_halo).
 
-    cand: (E, Np) candidate mask; global_id/g2l/gstart: this rank's LOCAL
-    numbering; numbering: the coordinate-numbering function (the reference's
-    rule).  Collective: one allgather of the candidates' coordinates.
+    xe, ye, ze, cand, global_id: (E', Np) arrays of the LEADING E' elements of this rank -- all of them,
+    or only those that touch a vertex shared with another rank (``interface_first_order`` puts them
+    first): every copy of an interface node lies in such an element and is itself a candidate, so the
+    interior of a slab never has to leave the device.  cand: candidate mask; global_id: this rank's
+    LOCAL numbering; numbering: the coordinate-numbering function (the reference's rule).
+    Collective: one allgather of the candidates' coordinates.
     """
     rank, size = comm.rank, comm.size
     empty = dict(nb_rank=np.zeros(0, np.int32), nb_count=np.zeros(0, np.int64), send_start=np.zeros(1, np.int64),
@@ -124,8 +127,13 @@ def build_halo(comm, xe, ye, ze, cand, global_id, g2l, gstart, numbering):
     if size == 1:
         return empty
     x, y, z = xe.reshape(-1), ye.reshape(-1), ze.reshape(-1)
-    uid = np.unique(global_id.reshape(-1)[cand.reshape(-1)]).astype(np.int64)  # local ids (1-based) of candidates
-    rep = g2l[gstart[uid - 1]]                                                # one local copy of each
+    # candidate copies grouped by local id, ascending local index inside a group (fixed summation order)
+    cpos = np.flatnonzero(cand.reshape(-1))
+    cgid = global_id.reshape(-1)[cpos].astype(np.int64)
+    by_id = np.argsort(cgid, kind="stable")
+    cpos, cgid = cpos[by_id], cgid[by_id]
+    uid, first, ncopy_all = np.unique(cgid, return_index=True, return_counts=True)
+    rep = cpos[first]                                                         # one local copy of each
     mine = np.stack([x[rep], y[rep], z[rep]], axis=1)
     parts = comm.allgather(mine)
     counts = np.array([p.shape[0] for p in parts], dtype=np.int64)
@@ -147,7 +155,7 @@ def build_halo(comm, xe, ye, ze, cand, global_id, g2l, gstart, numbering):
     me = owner == rank
     order = np.argsort(grp[me], kind="stable")
     g_mine = grp[me][order]                     # my interface nodes, ascending group id (canonical order)
-    uid_mine = uid[pos[me][order]]
+    idx_mine = pos[me][order]                   # their rows in uid / first / ncopy_all
     n_if = g_mine.size
     if n_if == 0:
         return empty
@@ -159,14 +167,12 @@ def build_halo(comm, xe, ye, ze, cand, global_id, g2l, gstart, numbering):
     n_send = m_o.size
     node_of = np.searchsorted(g_mine, g_o)      # my node behind each send entry
     nb_rank, nb_count = np.unique(m_o, return_counts=True)
-    # local copies per interface node
-    lo, hi = gstart[uid_mine - 1], gstart[uid_mine]
-    ncopy = (hi - lo).astype(np.int64)
+    # local copies per interface node (ascending local index)
+    lo = first[idx_mine]
+    ncopy = ncopy_all[idx_mine].astype(np.int64)
     copy_start = np.concatenate(([0], np.cumsum(ncopy)))
     flat = np.repeat(lo - copy_start[:-1], ncopy) + np.arange(copy_start[-1])
-    copy_ids = g2l[flat]
-    # ascending local index inside each node (fixed summation order)
-    copy_ids = copy_ids[np.lexsort((copy_ids, np.repeat(np.arange(n_if), ncopy)))]
+    copy_ids = cpos[flat]
     # send entries -> the copies of their node
     ns = ncopy[node_of]
     send_start = np.concatenate(([0], np.cumsum(ns)))

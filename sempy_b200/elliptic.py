@@ -52,8 +52,7 @@ def elliptic_ax(mesh, p):
 
 
 def _cg(mesh, b, tol, maxit, verbose, precond, out=None):
-    need = ("D", "geom", "gs", "mask") if mesh.mask is not None else ("D", "geom", "gs")
-    ctx = mesh._context(need=need)
+    ctx = mesh._context(need=("D", "geom", "gs"))  # the mask is optional: applied when setup_mask() has run
     bin_, x, mem = _new_like(mesh, b, "elliptic_cg")
     if out is not None:
         # caller-provided result buffer (e.g. pinned host memory); same kind as b

@@ -176,6 +176,7 @@ class _Context:
         handle = C.c_void_p()
         _capi.check(self.lib.semb_create(C.byref(handle), device, nelem, Nq))
         self.handle = handle
+        self.have = set()  # which parts of the operator state are set: "D", "geom", "gs", "mask"
 
     def __del__(self):
         try:
@@ -184,6 +185,30 @@ class _Context:
                 self.handle = None
         except Exception:
             pass
+
+
+class _NodeArray:
+    """A mesh array that lives on the device, on the host, or on both (mirrored on first request).
+    Set-up keeps everything on the device; the host copy only exists if somebody asks for it
+    (``mesh.xe``, ``mesh.get_x()``, ``mesh.global_id`` ... as the reference's callers do)."""
+
+    def __init__(self, host=None, dev=None, count=None, shape=None):
+        self._host, self._dev, self._count, self._shape = host, dev, count, shape
+
+    def host(self):
+        if self._host is None:
+            h = self._dev.to_host(self._count)
+            self._host = h.reshape(self._shape) if self._shape is not None else h
+        return self._host
+
+    def dev(self):
+        if self._dev is None:
+            self._dev = _capi.DevBuf.from_host(self._host)
+        return self._dev
+
+    @property
+    def ptr(self):
+        return self.dev().ptr
 
 
 class Mesh:
@@ -199,7 +224,7 @@ class Mesh:
     @classmethod
     def from_arrays(cls, points, hexes, debug=0, comm=None):
         """Build from vertex coordinates (nv,3) and hexahedra (E,8) in gmsh order.
-        With a multi-rank ``comm`` every rank passes the WHOLE mesh and keeps
+        With a multi-rank ``comm`` every rank passes the WHOLE (vertex-level) mesh and keeps
         its own contiguous slab of elements (see sempy_b200/distributed.py)."""
         self = cls.__new__(cls)
         self.debug = debug
@@ -210,10 +235,11 @@ class Mesh:
 
     def _reset_device_state(self):
         self._ctx = None
-        self._dirty = {"D": True, "geom": True, "gs": True, "mask": True}
-        self.geom6 = None
-        self.global_to_local = None
-        self.mask = None
+        self._coords = [None, None, None]
+        self._gid = self._g2l = self._gst = None
+        self._geom6_host = self._mask_host = self._rmult_host = None
+        self._jaco = None
+        self.num_unique = None
 
     def read(self, fname):
         points, hexes, nquads = read_gmsh22(fname)
@@ -278,41 +304,146 @@ class Mesh:
     def get_num_face_verts(self):
         return self.nface_verts
 
+    # -- node arrays: device resident, host copies on request ---------------------
+    def _coord_get(self, axis):
+        a = self._coords[axis]
+        if a is None:
+            raise AttributeError("call find_physical_coordinates() first")
+        return a.host()
+
+    def _coord_set(self, axis, value):
+        value = _capi.as_f64(value)
+        self._coords[axis] = _NodeArray(host=value.reshape(self.num_elements, -1))
+
+    xe = property(lambda self: self._coord_get(0), lambda self, v: self._coord_set(0, v))
+    ye = property(lambda self: self._coord_get(1), lambda self, v: self._coord_set(1, v))
+    ze = property(lambda self: self._coord_get(2), lambda self, v: self._coord_set(2, v))
+
+    def _numbering_get(self, which):
+        a = getattr(self, which)
+        if a is None:
+            raise AttributeError("call establish_global_numbering() first")
+        return a.host()
+
+    def _numbering_set(self, which, value, dtype):
+        setattr(self, which, None if value is None else _NodeArray(host=np.ascontiguousarray(value, dtype=dtype)))
+
+    global_id = property(lambda self: self._numbering_get("_gid"), lambda self, v: self._numbering_set("_gid", v, np.int32))
+    global_to_local = property(lambda self: self._numbering_get("_g2l"),
+                               lambda self, v: self._numbering_set("_g2l", v, np.int64))
+    global_start = property(lambda self: self._numbering_get("_gst"), lambda self, v: self._numbering_set("_gst", v, np.int64))
+
+    @property
+    def geom6(self):
+        """(E,6,Np): the six distinct geometric factors rr, rs, rt, ss, st, tt (host copy of the device array)."""
+        if self._geom6_host is None:
+            ctx = self._context(need=("geom",))
+            g6 = np.empty((self.num_elements, 6, self.Np))
+            _capi.check(ctx.lib.semb_get_geom(ctx.handle, g6.ctypes.data, _capi.HOST))
+            self._geom6_host = g6
+        return self._geom6_host
+
+    @geom6.setter
+    def geom6(self, value):
+        g6 = _capi.as_f64(value).reshape(self.num_elements, 6, self.Np)
+        ctx = self._context(need=())
+        _capi.check(ctx.lib.semb_set_geom(ctx.handle, g6.ctypes.data, _capi.G6, _capi.HOST))
+        ctx.have.add("geom")
+        self._geom6_host = g6
+
+    @property
+    def geom(self):
+        """(E,3,3,Np) view of the geometric factors as the reference stores them."""
+        return self.geom6[:, [[0, 1, 2], [1, 3, 4], [2, 4, 5]], :]
+
+    @property
+    def jaco(self):
+        if self._jaco is None:
+            raise AttributeError("call calc_geometric_factors() first")
+        return self._jaco.host()
+
+    @property
+    def mass(self):
+        return np.broadcast_to(self._B, (self.num_elements, self.Np))
+
+    @property
+    def mask(self):
+        """0.0 at Dirichlet nodes, 1.0 elsewhere (sempy/mesh.py:459-475); None before setup_mask()."""
+        if self._mask_host is None and self._ctx is not None and "mask" in self._ctx.have:
+            ctx = self._ctx
+            m = np.empty(self.num_elements * self.Np)
+            _capi.check(ctx.lib.semb_get_mask(ctx.handle, m.ctypes.data, _capi.HOST))
+            self._mask_host = m
+        return self._mask_host
+
+    @mask.setter
+    def mask(self, value):
+        self._mask_host = None if value is None else _capi.as_f64(value).reshape(-1)
+        if value is not None and self._ctx is not None:
+            ids = np.ascontiguousarray(np.flatnonzero(self._mask_host == 0), dtype=np.int64)
+            _capi.check(self._ctx.lib.semb_set_mask(self._ctx.handle, ids.ctypes.data, ids.size))
+            self._ctx.have.add("mask")
+
+    @property
+    def rmult(self):
+        if self._rmult_host is None:
+            ctx = self._context(need=("gs",))
+            r = np.empty(self.num_elements * self.Np)
+            _capi.check(ctx.lib.semb_get_rmult(ctx.handle, r.ctypes.data, _capi.HOST))
+            self._rmult_host = r
+        return self._rmult_host
+
+    def device_array(self, name):
+        """Device-resident array as an object with ``__cuda_array_interface__`` (wrap it with
+        ``torch.as_tensor(a, device="cuda")``; no copy): "x", "y", "z", "jaco", "global_id"."""
+        src = {"x": self._coords[0], "y": self._coords[1], "z": self._coords[2], "jaco": self._jaco, "global_id": self._gid}[name]
+        if src is None:
+            raise RuntimeError(f"{name} is not set up yet")
+        return src.dev()
+
     # -- set-up ---------------------------------------------------------------
     def find_physical_coordinates(self, N):
         """GLL coordinates by trilinear interpolation of the 8 vertices
-        (sempy/mesh.py:247-302): one batched kron launch per coordinate."""
+        (sempy/mesh.py:247-302): one batched kron launch per coordinate, results stay on the device."""
         self.N = N
         self.Nq = N + 1
         self.Nfp = (N + 1) * (N + 1)
         self.Np = (N + 1) ** 3
+        self._reset_device_state()
         z_1, _ = gauss_lobatto(1)
         z_N, _ = gauss_lobatto(N)
-        J = lagrange(z_N, z_1)
-        self.xe = kron(J, J, J, self.x[:, _GMSH_TO_LEX])
-        self.ye = kron(J, J, J, self.y[:, _GMSH_TO_LEX])
-        self.ze = kron(J, J, J, self.z[:, _GMSH_TO_LEX])
-        self._reset_device_state()
+        J = _capi.as_f64(lagrange(z_N, z_1))
+        ctx = self._context(need=())
+        if not device_setup_enabled():
+            for axis, v in enumerate((self.x, self.y, self.z)):
+                self._coord_set(axis, kron(J, J, J, v[:, _GMSH_TO_LEX]))
+            return
+        E, Nq = self.num_elements, self.Nq
+        for axis, v in enumerate((self.x, self.y, self.z)):
+            verts = _capi.DevBuf.from_host(_capi.as_f64(v[:, _GMSH_TO_LEX]), device=ctx.device)
+            out = _capi.DevBuf((E, self.Np), np.float64, device=ctx.device)
+            _capi.check(ctx.lib.semb_kron(ctx.device, J.ctypes.data, Nq, 2, J.ctypes.data, Nq, 2, J.ctypes.data, Nq, 2, E,
+                                          verts.ptr, out.ptr, _capi.DEVICE))
+            self._coords[axis] = _NodeArray(dev=out)
 
     def calc_geometric_factors(self):
-        """G = (grad a . grad b) B J, Jacobian and mass per node
-        (sempy/mesh.py:304-356), vectorised over all elements; the nine
-        coordinate derivatives come from the batched GPU gradient."""
+        """G = (grad a . grad b) B J, Jacobian and mass per node (sempy/mesh.py:304-356): one fused kernel
+        (nine coordinate derivatives + the metric formulas per node) writing straight into the operator's
+        device array; nothing of G crosses PCIe."""
         n = self.Nq
-        D = reference_derivative_matrix(self.N)
-        if device_setup_enabled():
-            # one fused kernel: nine derivatives and the metric formulas per node (semb_geom_factors)
-            lib = _capi.lib()
-            E, Np = self.xe.shape
+        D = _capi.as_f64(reference_derivative_matrix(self.N))
+        self._B = reference_mass_matrix_3d(self.N)
+        self._geom6_host = None
+        E, Np = self.num_elements, self.Np
+        if self._ctx is not None and device_setup_enabled():
+            ctx = self._context(need=())
             _, w = gauss_lobatto(self.N)
-            D, w = _capi.as_f64(D), _capi.as_f64(w)
-            g6 = np.empty((E, 6, Np))
-            J = np.empty((E, Np))
-            xe, ye, ze = (_capi.as_f64(c) for c in (self.xe, self.ye, self.ze))
-            _capi.check(lib.semb_geom_factors(_capi.current_device(), n, D.ctypes.data, w.ctypes.data, E, xe.ctypes.data,
-                                              ye.ctypes.data, ze.ctypes.data, g6.ctypes.data, J.ctypes.data, _capi.HOST))
-            self.geom6, self.jaco, self._B = g6, J, reference_mass_matrix_3d(self.N)
-            self._dirty["geom"] = True
+            w = _capi.as_f64(w)
+            jac = _capi.DevBuf((E, Np), np.float64, device=ctx.device)
+            _capi.check(ctx.lib.semb_setup_geom(ctx.handle, w.ctypes.data, self._coords[0].ptr, self._coords[1].ptr,
+                                                self._coords[2].ptr, jac.ptr, _capi.DEVICE))
+            self._jaco = _NodeArray(dev=jac)
+            ctx.have.add("geom")
             return
         xr, xs, xt = gradient(self.xe, n, D)
         yr, ys, yt = gradient(self.ye, n, D)
@@ -328,8 +459,7 @@ class Mesh:
         sz = -(xr * yt - xt * yr) / J
         tz = (xr * ys - xs * yr) / J
         del xr, xs, xt, yr, ys, yt, zr, zs, zt
-        B = reference_mass_matrix_3d(self.N)
-        E, Np = self.xe.shape
+        B = self._B
         g6 = np.empty((E, 6, Np))
         g6[:, 0] = (rx * rx + ry * ry + rz * rz) * B * J
         g6[:, 1] = (rx * sx + ry * sy + rz * sz) * B * J
@@ -337,76 +467,101 @@ class Mesh:
         g6[:, 3] = (sx * sx + sy * sy + sz * sz) * B * J
         g6[:, 4] = (sx * tx + sy * ty + sz * tz) * B * J
         g6[:, 5] = (tx * tx + ty * ty + tz * tz) * B * J
+        self._jaco = _NodeArray(host=J)
         self.geom6 = g6
-        self.jaco = J
-        self._B = B
-        self._dirty["geom"] = True
-
-    @property
-    def geom(self):
-        """(E,3,3,Np) view of the geometric factors as the reference stores them."""
-        return self.geom6[:, [[0, 1, 2], [1, 3, 4], [2, 4, 5]], :]
-
-    @property
-    def mass(self):
-        return np.broadcast_to(self._B, (self.num_elements, self.Np))
 
     def establish_global_numbering(self):
-        """Global ids by coordinate sort (sempy/mesh.py:389-442); the gslib
-        handle of the reference becomes the device gather-scatter schedule."""
-        number = global_numbering_device if device_setup_enabled() else global_numbering_from_coordinates
-        self.global_id, self.global_to_local, self.global_start = number(self.xe, self.ye, self.ze)
+        """Global ids by coordinate sort (sempy/mesh.py:389-442) and, taking the place of the reference's
+        gslib handle, the device gather-scatter schedule -- numbering, schedule and multiplicities are all
+        built on the device from the device-resident coordinates."""
+        ctx = self._context(need=())
+        lib = ctx.lib
+        n = self.num_elements * self.Np
+        self._rmult_host = None
+        if device_setup_enabled():
+            gid = _capi.DevBuf((self.num_elements, self.Np), np.int32, device=ctx.device)
+            g2l = _capi.DevBuf(n, np.int64, device=ctx.device)
+            gst = _capi.DevBuf(n + 1, np.int64, device=ctx.device)
+            ng = C.c_int64(0)
+            _capi.check(lib.semb_numbering(ctx.device, n, self._coords[0].ptr, self._coords[1].ptr, self._coords[2].ptr, 1e-12,
+                                           gid.ptr, g2l.ptr, gst.ptr, C.byref(ng), _capi.DEVICE))
+            self.num_unique = int(ng.value)
+            self._gid, self._g2l = _NodeArray(dev=gid), _NodeArray(dev=g2l)
+            self._gst = _NodeArray(dev=gst, count=self.num_unique + 1)
+            _capi.check(lib.semb_set_gather_scatter(ctx.handle, g2l.ptr, gst.ptr, self.num_unique, _capi.DEVICE))
+        else:
+            self.global_id, self.global_to_local, self.global_start = global_numbering_from_coordinates(self.xe, self.ye, self.ze)
+            self._upload_numbering(ctx)
+        ctx.have.add("gs")
         if self.comm.size > 1:
-            # ids are local to the rank; nodes with copies on other ranks go into the halo tables
-            cand = distributed.candidate_node_mask(self.elem_to_vert_map, self._shared_vertex, self.N)
-            self._halo = distributed.build_halo(self.comm, self.xe, self.ye, self.ze, cand, self.global_id,
-                                                self.global_to_local, self.global_start,
-                                                global_numbering_from_coordinates)
-        self._dirty["gs"] = True
-        self.rmult = np.empty(self.num_elements * self.Np, dtype=np.float64)
-        ctx = self._context(need=("gs",))
-        _capi.check(ctx.lib.semb_get_rmult(ctx.handle, self.rmult.ctypes.data, _capi.HOST))
+            self._build_halo()
+            self._attach_halo(ctx)
+
+    def _upload_numbering(self, ctx):
+        g2l, gst = self.global_to_local, self.global_start
+        self.num_unique = int(gst.size - 1)
+        _capi.check(ctx.lib.semb_set_gather_scatter(ctx.handle, g2l.ctypes.data, gst.ctypes.data, gst.size - 1, _capi.HOST))
+
+    def _build_halo(self):
+        """Interface tables: only the leading ``_n_if_elems`` elements (those touching a vertex shared with
+        another rank) can hold interface nodes, so only their coordinates and ids come to the host."""
+        ne, Np = self._n_if_elems, self.Np
+        cand = distributed.candidate_node_mask(self.elem_to_vert_map[:ne], self._shared_vertex, self.N)
+        lead = []
+        for a in (*self._coords, self._gid):
+            if a._host is not None:
+                lead.append(a._host.reshape(self.num_elements, Np)[:ne])
+            else:
+                lead.append(a._dev.to_host(ne * Np).reshape(ne, Np))
+        self._halo = distributed.build_halo(self.comm, lead[0], lead[1], lead[2], cand, lead[3],
+                                            global_numbering_from_coordinates)
 
     def setup_mask(self):
-        bbox = None
+        """Homogeneous Dirichlet mask of the bounding box (sempy/mesh.py:449-477); with several ranks the box
+        of the whole mesh."""
+        self._mask_host = None
+        if self._ctx is None or not device_setup_enabled():
+            bbox = None
+            if self.comm.size > 1:
+                ext = self.comm.allgather([(float(c.min()), float(c.max())) for c in (self.xe, self.ye, self.ze)])
+                bbox = [(min(e[a][0] for e in ext), max(e[a][1] for e in ext)) for a in range(3)]
+            self.mask = bounding_box_mask(self.xe, self.ye, self.ze, bbox=bbox)
+            return
+        ctx = self._ctx
+        n = self.num_elements * self.Np
+        ext = []
+        for a in self._coords:
+            lo_hi = np.empty(2)
+            _capi.check(ctx.lib.semb_minmax(ctx.device, n, a.ptr, lo_hi.ctypes.data, _capi.DEVICE))
+            ext.append((float(lo_hi[0]), float(lo_hi[1])))
         if self.comm.size > 1:
-            ext = self.comm.allgather([(float(c.min()), float(c.max())) for c in (self.xe, self.ye, self.ze)])
-            bbox = [(min(e[a][0] for e in ext), max(e[a][1] for e in ext)) for a in range(3)]
-        self.mask = bounding_box_mask(self.xe, self.ye, self.ze, bbox=bbox)
-        self._dirty["mask"] = True
+            every = self.comm.allgather(ext)
+            ext = [(min(e[a][0] for e in every), max(e[a][1] for e in every)) for a in range(3)]
+        bbox6 = _capi.as_f64([v for pair in ext for v in pair])
+        _capi.check(ctx.lib.semb_setup_mask_box(ctx.handle, self._coords[0].ptr, self._coords[1].ptr, self._coords[2].ptr,
+                                                bbox6.ctypes.data, 1e-8, _capi.DEVICE))
+        ctx.have.add("mask")
 
     # -- device context ---------------------------------------------------------
+    _NEED_HINT = {"geom": "calc_geometric_factors()", "gs": "establish_global_numbering()", "mask": "setup_mask()"}
+
     def _context(self, need=("D", "geom", "gs", "mask")):
+        """The semb_ctx of this mesh (created with the order N known); raises if a part of the operator
+        state that the caller needs has not been set up."""
         if self._ctx is None:
+            if not hasattr(self, "Nq"):
+                raise RuntimeError("call find_physical_coordinates(N) first")
             self._ctx = _Context(_capi.current_device(), self.num_elements, self.Nq)
-            self._dirty = {k: True for k in self._dirty}
-        ctx, lib = self._ctx, self._ctx.lib
+            D = _capi.as_f64(reference_derivative_matrix(self.N))
+            _capi.check(self._ctx.lib.semb_set_derivative(self._ctx.handle, D.ctypes.data))
+            self._ctx.have.add("D")
+            # host-side state set before the context existed (CPU-prepared meshes)
+            if self._mask_host is not None:
+                self.mask = self._mask_host
         for key in need:
-            if not self._dirty[key]:
-                continue
-            if key == "D":
-                D = _capi.as_f64(reference_derivative_matrix(self.N))
-                _capi.check(lib.semb_set_derivative(ctx.handle, D.ctypes.data))
-            elif key == "geom":
-                if self.geom6 is None:
-                    raise RuntimeError("call calc_geometric_factors() first")
-                g6 = _capi.as_f64(self.geom6)
-                _capi.check(lib.semb_set_geom(ctx.handle, g6.ctypes.data, _capi.G6, _capi.HOST))
-            elif key == "gs":
-                if self.global_to_local is None:
-                    raise RuntimeError("call establish_global_numbering() first")
-                g2l = np.ascontiguousarray(self.global_to_local, dtype=np.int64)
-                gst = np.ascontiguousarray(self.global_start, dtype=np.int64)
-                _capi.check(lib.semb_set_gather_scatter(ctx.handle, g2l.ctypes.data, gst.ctypes.data, gst.size - 1))
-                if self.comm.size > 1:
-                    self._attach_halo(ctx)
-            elif key == "mask":
-                if self.mask is None:
-                    raise RuntimeError("call setup_mask() first")
-                ids = np.ascontiguousarray(self.get_mask_ids(), dtype=np.int64)
-                _capi.check(lib.semb_set_mask(ctx.handle, ids.ctypes.data, ids.size))
-            self._dirty[key] = False
-        return ctx
+            if key not in self._ctx.have:
+                raise RuntimeError(f"call {self._NEED_HINT.get(key, key)} first")
+        return self._ctx
 
     def _attach_halo(self, ctx):
         """NCCL communicator (once per context) and this rank's interface tables."""
@@ -424,7 +579,7 @@ class Mesh:
         _capi.check(lib.semb_set_halo(ctx.handle, keep[0].size, keep[0].ctypes.data, keep[1].ctypes.data,
                                       keep[2].ctypes.data, keep[3].ctypes.data, h["n_if"], keep[4].ctypes.data,
                                       keep[5].ctypes.data, keep[6].ctypes.data, keep[7].ctypes.data, self._n_if_elems))
-        if os.environ.get("SEMB_P2P", "1") != "0" and not getattr(ctx, "p2p_ready", False):
+        if os.environ.get("SEMB_P2P", "1") != "0":
             # peer-memory transport: publish this rank's receive region, map everybody else's
             handle = C.create_string_buffer(64)
             cap = max(self.comm.allgather(int(keep[3].size and h["send_start"].size - 1)))
@@ -434,7 +589,6 @@ class Mesh:
             peer_off = distributed.peer_receive_offsets([(e[1], e[2]) for e in everyone], self.comm.rank, h["nb_rank"])
             blob = b"".join(e[0] for e in everyone)
             _capi.check(lib.semb_p2p_attach(ctx.handle, blob, peer_off.ctypes.data))
-            ctx.p2p_ready = True
 
     def _vector_args(self, x, name):
         """(pointer, mem flag, keep-alive) for an in-place vector argument."""
@@ -444,6 +598,8 @@ class Mesh:
 
             if x.dtype != torch.float64 or not x.is_contiguous() or x.numel() != size:
                 raise ValueError(f"{name}: need a contiguous float64 CUDA tensor of {size} entries")
+            if x.data_ptr() % 16:
+                raise ValueError(f"{name}: CUDA tensors must be 16-byte aligned (a view with an odd element offset is not)")
             return x.data_ptr(), _capi.DEVICE, x
         if not isinstance(x, np.ndarray) or x.dtype != np.float64 or not x.flags.c_contiguous or x.size != size:
             raise ValueError(f"{name}: need a C-contiguous float64 NumPy array of {size} entries")
@@ -520,6 +676,7 @@ class _DeviceOperator:
     def apply_device(self, d_in, d_out, n):
         need = ["D", "geom"] + (["mask"] if self.flags & _capi.AX_MASK else []) + (["gs"] if self.flags & _capi.AX_GS else [])
         ctx = self.mesh._context(need=tuple(need))
+        _capi.check(ctx.lib.semb_set_stream(ctx.handle, None))
         _capi.check(ctx.lib.semb_ax(ctx.handle, d_in, d_out, self.flags, _capi.DEVICE))
         _capi.check(ctx.lib.semb_synchronize(ctx.handle))
 

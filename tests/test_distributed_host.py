@@ -67,7 +67,8 @@ def _worker(rank, size, port, dims, perturb, N, out):
         m.xe, m.ye, m.ze = so.physical_coordinates(m.x, m.y, m.z, N)
         m.global_id, m.global_to_local, m.global_start = pm.global_numbering_from_coordinates(m.xe, m.ye, m.ze)
         cand = dd.candidate_node_mask(m.elem_to_vert_map, m._shared_vertex, N)
-        halo = dd.build_halo(comm, m.xe, m.ye, m.ze, cand, m.global_id, m.global_to_local, m.global_start,
+        ne = m._n_if_elems  # only the leading interface elements are handed over, as Mesh._build_halo does
+        halo = dd.build_halo(comm, m.xe[:ne], m.ye[:ne], m.ze[:ne], cand[:ne], m.global_id[:ne],
                              pm.global_numbering_from_coordinates)
         # global reference: the whole mesh numbered at once, seeded vector
         gxe, gye, gze = so.physical_coordinates(*so.element_vertices(pts, hexes), N)

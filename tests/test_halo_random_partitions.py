@@ -53,7 +53,7 @@ def run_partition(dims, N, size, perturb, seed):
             xe, ye, ze = gxe[lo:hi], gye[lo:hi], gze[lo:hi]
             gid, l2l, ls = pm.global_numbering_from_coordinates(xe, ye, ze)
             cand = dd.candidate_node_mask(hexes[lo:hi], shared_v, N)
-            halo = dd.build_halo(comm, xe, ye, ze, cand, gid, l2l, ls, pm.global_numbering_from_coordinates)
+            halo = dd.build_halo(comm, xe, ye, ze, cand, gid, pm.global_numbering_from_coordinates)
             got = dd.emulate_gather_scatter(comm, halo, xg.reshape(E, Np)[lo:hi].reshape(-1), l2l, ls)
             errs[rank] = float(np.abs(got - ref[lo:hi].reshape(-1)).max() / np.abs(ref).max())
             info[rank] = (int(halo["n_if"]), len(halo["nb_rank"]), int(np.diff(halo["src_start"]).max()) if halo["n_if"] else 0)
