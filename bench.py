@@ -2,16 +2,20 @@
 """Benchmark of the SemPy Poisson hot path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--nel n] [--order N] [--perturb d] [--strong n]
 
-A *step* is one Jacobi-PCG solve (tol 1e-8) of the 3-D Poisson problem on a
-box mesh of 32^3 elements at N=7 (BASELINE config 2; 16.8 M local
-nodes per GPU), i.e. ~50 passes of the hot path (fused Ax + mask + local pAp,
-gather-scatter, fused vector updates).  ``value`` is local DOF x iterations per
-second with everything resident in HBM; ``e2e`` is the same solve called through
-the drop-in API with HOST (pinned) NumPy buffers, host<->device copies timed.
-``roofline`` describes the dominant kernel (the fused Ax), timed live with CUDA
-events inside the timed region.  ``--impl reference`` times the CPU oracle (a
-C/OpenMP restatement of the reference's algorithm, all host cores) on a bounded sample.
+A *step* is one Jacobi-PCG solve (tol 1e-8) of the 3-D Poisson problem of the reference's poisson.py on
+a box mesh: by default 32^3 elements at N=7 (BASELINE config 2; 16.8 M local nodes per GPU), i.e. ~45
+passes of the hot path (fused direction update + Ax + mask + local pAp, gather-scatter, fused vector
+update with the dot products).  ``value`` is local DOF x iterations per second with everything resident
+in HBM; ``e2e`` is the same solve through the reference-facing call ``elliptic_pcg(mesh, b) -> x`` with
+HOST NumPy arrays, host<->device copies timed.  ``roofline`` describes the dominant kernel, timed live
+with CUDA events inside the timed region.  Other BASELINE configs: ``--order 15 --nel 32`` (config 3),
+``--strong 64 --perturb 0.3`` (config 4), ``--nel 48`` on 1/2/4/8 GPUs (config 5).
+
+``--impl reference`` times the reference's algorithm on the host cores: its C/OpenMP restatement
+(oracle/c/sem_oracle.c) with all threads on the same mesh, set up by the oracle's own NumPy code --
+nothing of sempy_b200 is imported on that arm.
 """
 
 from __future__ import annotations
@@ -29,33 +33,36 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NQ = 8
 N_ORDER = 7
-F_SHARED = 1.0 - ((N_ORDER - 1) / (N_ORDER + 1)) ** 3
-BYTES_AX = 64.0                      # u 8 + six G 48 + w 8 per local node
-BYTES_GS = 20.0 * F_SHARED           # shared nodes: read 8 + index 4 + write 8
-BYTES_UPDATE_PCG = 49.0 + 8.0        # x,p,r,Ap reads 32 + 1-byte multiplicity + x,r writes 16 (+ dinv 8)
-BYTES_DIR_PCG = 24.0 + 8.0           # r,p reads + p write (+ dinv)
 TOL = 1e-8
+CPU_ITERS = 10  # PCG iterations per CPU step: a bounded sample of the ~45-iteration solve
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the fused Ax kernel from the committed ncu capture
-    (profiles/ax_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
-    path = os.path.join(ROOT, "profiles", "ax_traffic.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh)
-    except Exception:
-        return None
+def f_shared(N):
+    return 1.0 - ((N - 1) / (N + 1)) ** 3
+
+
+# Algorithmic bytes per local node (Ax 64, gather-scatter 20 per shared node, CG vector work)
+BYTES_AX = 64.0            # u 8 + six G 48 + w 8
+BYTES_AX_DIR = 88.0        # + the folded direction update p <- dinv r + beta p: r 8, dinv 8, p written 8
+BYTES_UPDATE = 57.0        # x, p, r, Ap reads 32 + dinv 8 + 1-byte multiplicity + x, r writes 16
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -129,44 +136,76 @@ class ClockSampler:
         return out
 
 
+def mesh_dims(nel, world, strong):
+    """Element counts of the whole box.  Weak scaling: nel^3 elements per GPU as z-slabs of a
+    (2 nel) x (2 nel) x (nel/4 * ranks) box, which ends at the (2 nel)^3 cube on 8 GPUs (BASELINE config 5:
+    nel = 48 -> 96^3).  Strong scaling: one strong^3 box for every rank count (config 4: 64)."""
+    if strong > 0:
+        return strong, strong, strong
+    if world > 1:
+        return 2 * nel, 2 * nel, (nel // 4) * world
+    return nel, nel, nel
+
+
+def workload_name(args, world):
+    nx, ny, nz = mesh_dims(args.nel, world, args.strong)
+    kind = "deformed" if args.perturb else "straight"
+    cfg = ("BASELINE config 4, strong scaling" if args.strong > 0 else
+           "BASELINE config 3" if N_ORDER == 15 else
+           "BASELINE config 5, weak scaling" if args.nel == 48 else
+           "BASELINE config 2" if (world == 1 and args.nel == 32 and N_ORDER == 7) else
+           "weak scaling of BASELINE config 2" if N_ORDER == 7 and args.nel == 32 else "custom size")
+    return f"3D Poisson, {kind} box {nx}x{ny}x{nz} elements, N={N_ORDER}, Jacobi-PCG tol 1e-8 ({cfg})"
+
+
 def build_problem(nel, perturb=0.0, comm=None, strong=0):
-    """Box mesh of nel^3 elements (deformed if perturb > 0) at N=7 plus the manufactured RHS of
-    the reference's poisson.py:27-40.  Returns (mesh, b_host).  strong > 0: a fixed strong^3-element box
-    shared by all ranks (BASELINE config 4: --strong 64 --perturb 0.3)."""
+    """Box mesh at order N_ORDER plus the manufactured RHS of the reference's poisson.py:27-40, everything
+    built on the device.  Returns (mesh, b, exact) with b and exact as CUDA tensors."""
+    import torch
+
     from sempy_b200.mesh import box_mesh
 
-    if strong > 0:
-        m = box_mesh(strong, perturb=perturb, seed=0, comm=comm)
-    elif comm is not None and comm.size > 1:
-        # weak scaling: nel^3 elements per GPU as z-slabs of a (2 nel) x (2 nel) x (nel/4 * ranks) box,
-        # which ends at the (2 nel)^3 cube on 8 GPUs (64^3 for nel = 32)
-        m = box_mesh(2 * nel, 2 * nel, (nel // 4) * comm.size, perturb=perturb, seed=0, comm=comm)
-    else:
-        m = box_mesh(nel, perturb=perturb, seed=0)
+    world = comm.size if comm is not None else 1
+    nx, ny, nz = mesh_dims(nel, world, strong)
+    m = box_mesh(nx, ny, nz, perturb=perturb, seed=0, comm=comm)
     m.find_physical_coordinates(N_ORDER)
     m.establish_global_numbering()
     m.calc_geometric_factors()
     m.setup_mask()
-    X, Y, Z = m.get_x(), m.get_y(), m.get_z()
-    b = 3 * np.pi * np.pi * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
-    b = b * m.get_mass() * m.get_jaco()
-    b = m.dssum(b)
-    b = m.apply_mask(b)
-    return m, b
+    dev = torch.device("cuda", torch.cuda.current_device())
+    X, Y, Z, J = (torch.as_tensor(m.device_array(k), device=dev).reshape(-1) for k in ("x", "y", "z", "jaco"))
+    exact = torch.sin(np.pi * X) * torch.sin(np.pi * Y) * torch.sin(np.pi * Z)
+    B = torch.from_numpy(np.array(m.mass[0], copy=True)).to(dev)
+    b = (3 * np.pi * np.pi * exact).reshape(-1, m.Np) * B * J.reshape(-1, m.Np)
+    b = b.reshape(-1).contiguous()
+    m.dssum(b)
+    m.apply_mask(b)
+    return m, b, exact
 
 
-def oracle_problem(mesh, b):
-    """Arrays of the SAME problem for the CPU oracle (the mesh set-up is input preparation, done once
-    through the product's mesh class; the timed CPU path is the oracle's)."""
-    from sempy_b200.derivative import reference_derivative_matrix
+# ---------------------------------------------------------------------------
+# CPU arms (oracle only; nothing of sempy_b200 is imported here)
+# ---------------------------------------------------------------------------
+def oracle_problem(nx, ny, nz, perturb, N):
+    """The same problem set up by the oracle's own NumPy restatement of the reference's mesh code."""
+    from oracle import sem_oracle as so
 
-    D = np.ascontiguousarray(reference_derivative_matrix(N_ORDER))
-    g2l, gs = mesh.get_global_to_local_map()
-    return dict(geom=np.ascontiguousarray(mesh.get_geom()), D=D, g2l=g2l, gs=gs, rmult=mesh.get_rmult().copy(),
-                mask=mesh.mask.copy(), b=np.array(b, copy=True), dof=mesh.get_num_elems() * mesh.Np)
+    pts, hexes = so.box_mesh(nx, ny, nz, perturb=perturb, seed=0)
+    xe, ye, ze = so.physical_coordinates(*so.element_vertices(pts, hexes), N)
+    _, g2l, gs = so.global_numbering(xe, ye, ze)
+    geom, jaco, mass = so.geometric_factors(xe, ye, ze, N)
+    rmult, mask = so.multiplicity_inverse(g2l, gs), so.dirichlet_mask(xe, ye, ze)
+    b = 3 * np.pi ** 2 * np.sin(np.pi * xe) * np.sin(np.pi * ye) * np.sin(np.pi * ze) * mass * jaco
+    b = so.gather_scatter(b.reshape(-1), g2l, gs) * mask
+    D = np.ascontiguousarray(so.reference_derivative_matrix(N))
+    return dict(geom=np.ascontiguousarray(geom), D=D, g2l=g2l, gs=gs, rmult=rmult, mask=mask, b=b, dof=xe.size)
 
 
-CPU_ITERS = 10  # PCG iterations per CPU step: a bounded sample of the ~45-iteration solve
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
 
 
 def time_oracle(prob, iters, steps, warmup):
@@ -190,36 +229,132 @@ def time_oracle(prob, iters, steps, warmup):
     return prob["dof"] * iters * steps / total / 1e9, total / steps * 1e3, co.num_threads()
 
 
+def time_numpy_reference(n=8, N=7, cg_iters=3):
+    """The UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py; meshio / gslib_wrapper replaced
+    by oracle/ref_stubs.py) on an n^3-element box: Ax + mask + dssum and elliptic_cg, one host core."""
+    from oracle import make_ref, ref_stubs
+    from oracle import sem_oracle as so
+
+    if not make_ref.available():
+        return None
+    ref_stubs.install(make_ref.DEST)
+    from sempy.elliptic import elliptic_ax, elliptic_cg
+    from sempy.mesh import Mesh
+
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "box.msh")
+        so.write_gmsh22(path, *so.box_mesh(n, n, n))
+        t0 = time.perf_counter()
+        mesh = Mesh(path)
+        mesh.find_physical_coordinates(N)
+        mesh.establish_global_numbering()
+        mesh.calc_geometric_factors()
+        mesh.setup_mask()
+        t_setup = time.perf_counter() - t0
+    dof = mesh.get_num_elems() * mesh.Np
+    X, Y, Z = mesh.get_x(), mesh.get_y(), mesh.get_z()
+    b = 3 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z) * mesh.get_mass() * mesh.get_jaco()
+    b = mesh.apply_mask(mesh.dssum(b))
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        mesh.dssum(mesh.apply_mask(elliptic_ax(mesh, b)))
+    t_ax = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    _, it = elliptic_cg(mesh, b, tol=1e-30, maxit=cg_iters)
+    t_cg = (time.perf_counter() - t0) / max(it, 1)
+    return {"value": dof / t_cg / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "reference",
+            "ax_gs_gdofs": dof / t_ax / 1e9, "setup_s": t_setup,
+            "sample": f"unmodified sempy (NumPy) from oracle/_ref on a {n}^3-element N={N} box ({dof} local DOF): "
+                      f"elliptic_cg, {it} iterations (unpreconditioned; the reference has no mesh-aware PCG), "
+                      f"and elliptic_ax + apply_mask + dssum x {reps}; one core (per-element Python loop); "
+                      "dssum is the stub of oracle/ref_stubs.py, not gslib"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mesh, b = build_problem(args.nel, args.perturb)
-    prob = oracle_problem(mesh, b)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    use_all_host_threads()
+    # bounded sample: the N-GPU mesh capped at one GPU's share (the CPU arm has one host to run on)
+    nx, ny, nz = mesh_dims(args.nel, 1, 0) if args.strong == 0 else (args.strong,) * 3
+    if args.strong > 0 or N_ORDER > 7:
+        # 134 M nodes need > 10 GB for G alone: sample an eighth of the box (same element shape)
+        nz = max(nz // 8, 1)
+    t0 = time.perf_counter()
+    prob = oracle_problem(nx, ny, nz, args.perturb, N_ORDER)
+    t_setup = time.perf_counter() - t0
     warm = min(args.warmup, 1)
     val, ms, threads = time_oracle(prob, CPU_ITERS, args.steps, warm)
-    sample = (f"C/OpenMP restatement of the reference algorithm (oracle/c/sem_oracle.c), {threads} threads, Jacobi-PCG on the "
-              f"full {args.nel}^3-element N={N_ORDER} mesh, {CPU_ITERS} iterations per step x {args.steps} steps")
+    sample = (f"C/OpenMP restatement of the reference algorithm (oracle/c/sem_oracle.c), {threads} threads, Jacobi-PCG on a "
+              f"{nx}x{ny}x{nz}-element N={N_ORDER} box ({prob['dof']} local DOF) set up by the oracle's NumPy code "
+              f"({t_setup:.0f} s), {CPU_ITERS} iterations per step x {args.steps} steps")
     line = {
         "impl": "reference", "metric": f"FP64 Jacobi-PCG Poisson throughput, N={N_ORDER} (local DOF x iterations / s)",
         "value": val, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {args.nel}^3 elements, N={N_ORDER}, Jacobi-PCG tol 1e-8 (BASELINE config 2)",
-                   "sample": f"{CPU_ITERS} PCG iterations per step on the full mesh",
-                   "note": "the reference is pure Python (~1 MDOF/s, one core) and cannot be shipped to the GPU box; "
-                           "this arm times its C/OpenMP restatement on all host cores"},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong > 0 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "sample": sample,
+                   "note": "throughput per host, independent of N: the CPU arm runs on rank 0's host cores only"},
         "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:
+        ref = time_numpy_reference()
+        if ref is not None:
+            line["cpu_baseline_reference"] = ref
+    except Exception as exc:  # the NumPy reference is an extra; never lose the line over it
+        line["cpu_baseline_reference"] = {"unavailable": repr(exc)}
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def small_vs_oracle(comm, world, rank):
+    """A deformed 4 x 4 x (2 ranks) box at N=7 solved by all ranks and compared with the CPU oracle on the
+    WHOLE mesh (rank 0): iteration count +-1, solution 1e-10 relative (the BASELINE tolerances)."""
+    from oracle import sem_oracle as so
+    from sempy_b200.elliptic import elliptic_pcg
+    from sempy_b200.mesh import box_mesh_arrays, Mesh
+
+    N = 7
+    dims = (4, 4, 2 * world)
+    pts, hexes = box_mesh_arrays(*dims, perturb=0.3, seed=2)
+    m = Mesh.from_arrays(pts, hexes, comm=comm)
+    m.find_physical_coordinates(N)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    E, Np = len(hexes), m.Np
+    gx, gy, gz = so.physical_coordinates(*so.element_vertices(pts, hexes), N)
+    _, g2l, gs = so.global_numbering(gx, gy, gz)
+    geom, jaco, mass = so.geometric_factors(gx, gy, gz, N)
+    rmult, mask = so.multiplicity_inverse(g2l, gs), so.dirichlet_mask(gx, gy, gz)
+    b = 3 * np.pi ** 2 * np.sin(np.pi * gx) * np.sin(np.pi * gy) * np.sin(np.pi * gz) * mass * jaco
+    b = so.gather_scatter(b.reshape(-1), g2l, gs) * mask
+    take = lambda v: np.ascontiguousarray(v.reshape(E, Np)[m.elem_global].reshape(-1))
+    D = np.ascontiguousarray(so.reference_derivative_matrix(N))
+    axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
+    dinv = mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
+    xo, ito = so.elliptic_pcg_jacobi(axo, dinv, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
+    xg, itg = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
+    if itg != ito:  # every rank sees the same counts: compare the iterates after the same number of steps
+        xg, _ = elliptic_pcg(m, take(b), tol=0.0, maxit=ito)
+    err = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
+    errs = comm.allgather(err) if world > 1 else [err]
+    return {"mesh": "deformed %dx%dx%d, N=7" % dims, "iters": int(itg), "oracle_iters": int(ito), "rel_err_max": max(errs),
+            "ok": bool(abs(itg - ito) <= 1 and max(errs) < 1e-10)}
+
+
 def run_ours(args):
+    import ctypes as C
+
     import torch
 
     from sempy_b200 import _capi, distributed
-    from sempy_b200.elliptic import elliptic_ax, elliptic_pcg
+    from sempy_b200.elliptic import _ax, elliptic_pcg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,24 +384,16 @@ def run_ours(args):
     peak, peak_kind = measured_peaks()
     nel = args.nel
     t_setup = time.perf_counter()
-    mesh, b_host = build_problem(nel, args.perturb, comm, args.strong)
+    mesh, b_dev, exact = build_problem(nel, args.perturb, comm, args.strong)
+    torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
     dof = mesh.get_num_elems() * mesh.Np
     ctx = mesh._context()
     lib = ctx.lib
-
-    b_dev = torch.from_numpy(b_host).cuda()
-    # pinned host buffers for the end-to-end arm
-    b_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
-    b_pin.copy_(torch.from_numpy(b_host))
-    x_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
-    b_pin_np, x_pin_np = b_pin.numpy(), x_pin.numpy()
+    p2p_on = world > 1 and os.environ.get("SEMB_P2P", "1") != "0"
 
     def solve_dev():
         return elliptic_pcg(mesh, b_dev, tol=TOL, maxit=1000)
-
-    def solve_host():
-        return elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
 
     # ---- device-resident arm -------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -274,7 +401,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         x_dev, niter = solve_dev()
     sync_all()
-    # inside the timed region only the dominant kernel (the fused Ax) is bracketed by events;
+    # inside the timed region only the dominant kernel (the fused operator) is bracketed by events;
     # the other kernels are timed in a second, untimed pass below (every bracket costs two event records)
     _capi.check(lib.semb_profile_enable(ctx.handle, 1 | ((1 << _capi.K_AX) << 1)))
     _capi.check(lib.semb_profile_reset(ctx.handle))
@@ -293,7 +420,6 @@ def run_ours(args):
     ms_total = over_ranks(ev0.elapsed_time(ev1), "MAX")
     dof_all = over_ranks(dof, "SUM")
     launches = lib.semb_launch_count(ctx.handle) - launches0
-    import ctypes as C
 
     def read_profile(names):
         out = {}
@@ -304,7 +430,7 @@ def run_ours(args):
         return out
 
     kern = read_profile([("ax", _capi.K_AX)])
-    # second pass (not part of `value`): all four kernel kinds bracketed
+    # second pass (not part of `value`): every kernel kind bracketed
     _capi.check(lib.semb_profile_enable(ctx.handle, 1))
     _capi.check(lib.semb_profile_reset(ctx.handle))
     ev0.record()
@@ -312,23 +438,26 @@ def run_ours(args):
     ev1.record()
     sync_all()
     ms_pass2 = ev0.elapsed_time(ev1)
-    kern2 = read_profile([("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE), ("direction", _capi.K_DIRECTION)])
+    kern2 = read_profile([("ax", _capi.K_AX), ("gs", _capi.K_GS), ("update", _capi.K_UPDATE)])
     _capi.check(lib.semb_profile_enable(ctx.handle, 0))
     value = dof_all * iters_total / (ms_total * 1e-3) / 1e9
-    # per CG iteration: with a halo the Ax of one iteration is two launches (interface elements, then the rest)
+    # per CG iteration: with a halo the operator of one iteration is two launches (interface elements, then the rest)
     ax_ms = kern["ax"][0] / max(iters_total, 1)
-    ax_gbs = BYTES_AX * dof / (ax_ms * 1e-3) / 1e9
+    ax_gbs = BYTES_AX_DIR * dof / (ax_ms * 1e-3) / 1e9
+    fs = f_shared(N_ORDER)
+    # the in-place pass only covers the segments with more than two copies; the pairs are summed by the update kernel
+    np1 = N_ORDER + 1
+    f_long = (12 * (N_ORDER - 1) + 8) / np1 ** 3
+    bytes_gs_long = 20.0 * f_long
 
-    def kernel_entry(name, bytes_per_dof):
+    def kernel_entry(name, bytes_per_dof, what):
         tot, cnt = kern2[name]
         ms = tot / max(iters_pass2, 1)
         gbs = bytes_per_dof * dof / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"ms_per_iteration": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs, "frac": gbs / peak,
-                "share_of_step": tot / ms_pass2}
+        return {"what": what, "ms_per_iteration": ms, "launches": cnt, "bytes_per_dof": bytes_per_dof, "achieved_gbs": gbs,
+                "frac": gbs / peak, "share_of_step": tot / ms_pass2}
 
     # ---- fused Ax + mask + gather-scatter alone (the north-star 70 % target) ----
-    from sempy_b200.elliptic import _ax
-
     p_dev = x_dev.clone()
     for _ in range(3):
         w = _ax(mesh, p_dev, _capi.AX_MASK | _capi.AX_GS)
@@ -341,22 +470,66 @@ def run_ours(args):
     sync_all()
     axgs_ms = over_ranks(ev0.elapsed_time(ev1), "MAX") / reps
     axgs_gdofs = dof_all / (axgs_ms * 1e-3) / 1e9
-    axgs_gbs = (BYTES_AX + BYTES_GS) * dof / (axgs_ms * 1e-3) / 1e9
+    axgs_gbs = (BYTES_AX + 20.0 * fs) * dof / (axgs_ms * 1e-3) / 1e9
+    del w, p_dev
 
-    # ---- end-to-end arm: host buffers through the public API ----------------
+    # ---- end-to-end arm: host arrays through the reference-facing call -------------
+    # (a) the drop-in call exactly as the reference's callers make it: a pageable NumPy b, a fresh NumPy x
+    b_host = b_dev.cpu().numpy()
     for _ in range(2):
-        solve_host()
+        x_host, _ = elliptic_pcg(mesh, b_host, tol=TOL, maxit=1000)
     sync_all()
     t0 = time.perf_counter()
     e_iters = 0
     for _ in range(args.steps):
-        _, it = solve_host()
+        x_host, it = elliptic_pcg(mesh, b_host, tol=TOL, maxit=1000)
         e_iters += it
     sync_all()
     e_s = over_ranks(time.perf_counter() - t0, "MAX")
     e2e_val = dof_all * e_iters / e_s / 1e9
-    # sanity: same answer on both arms and a solved problem
-    assert np.allclose(x_pin_np, x_dev.cpu().numpy(), rtol=0, atol=1e-12)
+    same_answer = bool(np.allclose(x_host, x_dev.cpu().numpy(), rtol=0, atol=1e-12))
+    # (b) the same call with caller-provided pinned buffers (out=, not in the reference's signature)
+    b_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
+    b_pin.copy_(torch.from_numpy(b_host))
+    x_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
+    b_pin_np, x_pin_np = b_pin.numpy(), x_pin.numpy()
+    for _ in range(2):
+        elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
+    sync_all()
+    t0 = time.perf_counter()
+    p_iters = 0
+    for _ in range(args.steps):
+        _, it = elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
+        p_iters += it
+    sync_all()
+    p_s = over_ranks(time.perf_counter() - t0, "MAX")
+    e2e_pinned = dof_all * p_iters / p_s / 1e9
+    del b_pin, x_pin, b_pin_np, x_pin_np, x_host, b_host
+
+    # ---- correctness of what was just timed: facts that do not depend on the rank count -------------
+    def maxabs(t):
+        return over_ranks(t.abs().max().item(), "MAX")
+
+    rm = torch.empty(dof, dtype=torch.float64, device="cuda")
+    _capi.check(lib.semb_get_rmult(ctx.handle, rm.data_ptr(), _capi.DEVICE))
+    err_exact = maxabs(x_dev - exact)
+    xc = x_dev.clone()
+    mesh.dssum(xc)
+    err_cont = maxabs(xc * rm - x_dev) / max(maxabs(x_dev), 1e-300)
+    xm = x_dev.clone()
+    mesh.apply_mask(xm)
+    boundary_zero = over_ranks(float(torch.equal(xm, x_dev)), "MIN") == 1.0
+    res = b_dev - _ax(mesh, x_dev, _capi.AX_MASK | _capi.AX_GS)
+    rnorm = np.sqrt(over_ranks(torch.dot(rm * res, res).item(), "SUM"))
+    bnorm = np.sqrt(over_ranks(torch.dot(rm * b_dev, b_dev).item(), "SUM"))
+    del xc, xm, res
+    check = {"manufactured_solution_max_err": err_exact, "continuity_rel": err_cont, "boundary_zero": boundary_zero,
+             "true_residual_rel": rnorm / bnorm, "host_and_device_arms_agree": same_answer,
+             "iterations": int(niter)}
+    check["ok"] = bool(err_exact < 1e-5 and err_cont < 1e-12 and boundary_zero and rnorm / bnorm < 1e-5 and same_answer)
+    if not args.no_oracle_check:
+        check["n_rank_solve_vs_oracle"] = small_vs_oracle(comm if world > 1 else distributed.SerialComm(), world, rank)
+        check["ok"] = bool(check["ok"] and check["n_rank_solve_vs_oracle"]["ok"])
 
     if world > 1:
         all_clocks = comm.allgather(clocks)
@@ -364,64 +537,85 @@ def run_ours(args):
         sm = [c["sm_mhz"] for c in all_clocks if c.get("sm_mhz")]
         clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": reasons,
                   "per_rank_sm_mhz": sm}
-    unique_local = int(mesh.global_start.size - 1)
+    unique_local = int(mesh.num_unique)
     if rank != 0:
         dist.destroy_process_group()
         return
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload (N = 1 only) ---
-    cpu_baseline = None
-    if world == 1 and dof <= 20e6:  # the CPU arm copies G as (E,3,3,Np): keep it to the default size
+    cpu_baseline = cpu_ref = None
+    if world == 1 and not args.no_cpu:
+        threads = use_all_host_threads()
         t_cpu0 = time.perf_counter()
-        prob = oracle_problem(mesh, b_host)
+        nx, ny, nz = mesh_dims(nel, 1, args.strong)
+        if dof > 20e6:
+            nz = max(nz // 8, 1)
+        prob = oracle_problem(nx, ny, nz, args.perturb, N_ORDER)
         cpu_val, _, threads = time_oracle(prob, CPU_ITERS, 2, 1)
         cpu_secs = time.perf_counter() - t_cpu0
         cpu_baseline = {"value": cpu_val, "unit": "GDOF/s", "cores": threads, "kind": "port",
                         "sample": "C/OpenMP restatement of the reference algorithm (oracle/c/sem_oracle.c), %d threads, "
-                                  "Jacobi-PCG on the same full mesh, %d iterations x 2 steps (%.0f s); the Python "
-                                  "reference itself runs ~1 MDOF/s on one core (BASELINE.md)" % (threads, CPU_ITERS, cpu_secs)}
+                                  "Jacobi-PCG on a %dx%dx%d-element N=%d box set up by the oracle's NumPy code, %d iterations x 2 "
+                                  "steps (%.0f s with set-up)" % (threads, nx, ny, nz, N_ORDER, CPU_ITERS, cpu_secs)}
         del prob
-    if args.strong > 0:
-        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {args.strong}^3 elements shared by "
-                    f"{world} GPU(s) in z-slabs, N={N_ORDER}, Jacobi-PCG tol 1e-8 (strong scaling, BASELINE config 4)")
-    elif world == 1:
-        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {nel}^3 elements, N={N_ORDER}, "
-                    "Jacobi-PCG tol 1e-8 (BASELINE config 2)")
-    else:
-        workload = (f"3D Poisson, {'deformed' if args.perturb else 'straight'} box {2 * nel}x{2 * nel}x{(nel // 4) * world} "
-                    f"elements in z-slabs of {nel ** 3} elements per GPU, N={N_ORDER}, Jacobi-PCG tol 1e-8 "
-                    "(weak scaling of BASELINE config 2; the 8-GPU mesh is the 64^3 box of config 4)")
+        try:
+            cpu_ref = time_numpy_reference()
+        except Exception as exc:
+            cpu_ref = {"unavailable": repr(exc)}
 
+    if world == 1:
+        parallelism = "1 GPU"
+    elif p2p_on:
+        parallelism = (f"{world} GPUs, one z-slab of elements per GPU (no data-path NCCL call): interface sums written straight "
+                       "into the neighbours' memory over NVLink (peer memory, LL words) while the interior elements are "
+                       "computed; the two dot products per iteration are summed over the ranks inside the kernels that "
+                       "produce them (peer-memory all-reduce)")
+    else:
+        parallelism = (f"{world} GPUs, one z-slab of elements per GPU, NCCL send/recv halo exchange on a second stream "
+                       "overlapped with the interior elements + ncclAllReduce of the dot products")
+    k1 = "ax8_kernel" if N_ORDER == 7 else "axl_kernel" if N_ORDER >= 8 else "ax_generic_kernel"
+    traffic = ncu_traffic(k1 + "_dir") if (world == 1 and nel == 32 and N_ORDER == 7) else None
     line = {
         "metric": f"FP64 Jacobi-PCG Poisson throughput, N={N_ORDER} (local DOF x iterations / s)",
         "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong > 0 else "weak",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload,
+        "config": {"workload": workload_name(args, world),
                    "elements_per_gpu": mesh.get_num_elems(), "local_dof_per_gpu": dof, "local_dof_total": int(dof_all),
                    "unique_dof_rank0": unique_local,
-                   "iterations_per_step": iters_total / args.steps, "cache": "inputs larger than L2 (G alone is %.0f MB per GPU)" % (48.0 * dof / 1e6),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one z-slab of elements per GPU, NCCL halo exchange overlapped with interior Ax + all-reduced dots",
-                   "setup_s": t_setup},
+                   "iterations_per_step": iters_total / args.steps,
+                   "cache": "inputs larger than L2 (G alone is %.0f MB per GPU)" % (48.0 * dof / 1e6),
+                   "parallelism": parallelism, "setup_s": t_setup},
         "cg_iters_per_s": iters_total / (ms_total * 1e-3),
-        "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + BYTES_GS, "achieved_gbs": axgs_gbs,
-                  "frac_of_hbm_roofline": axgs_gbs / peak, "what": "fused Ax+mask kernel followed by gather-scatter, device resident"},
-        "roofline": {"bound": "hbm", "kernel": ("ax8_kernel" if N_ORDER == 7 else "axl_kernel" if N_ORDER >= 8 else "ax_generic_kernel") + " (fused Ax + mask + local pAp)", "achieved": ax_gbs, "peak": peak,
-                     "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak,
-                     "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if world == 1 and nel == 32 and N_ORDER == 7 else None,
-                     "traffic_source": (ncu_traffic() or {}).get("source"), "algorithmic_bytes_per_launch": BYTES_AX * dof,
-                     "bytes_per_dof": BYTES_AX, "avg_ms": ax_ms, "avg_ms_is": "per CG iteration", "launches_timed": kern["ax"][1],
+        "us_per_iteration": ms_total / max(iters_total, 1) * 1e3,
+        "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + 20.0 * fs, "achieved_gbs": axgs_gbs,
+                  "frac_of_hbm_roofline": axgs_gbs / peak,
+                  "what": "semb_ax(MASK | GS): fused Ax + mask kernel followed by the in-place gather-scatter, device resident"},
+        "roofline": {"bound": "hbm", "kernel": k1 + "<MASK, DOT, DIR=2> (direction update + Ax + mask + local pAp in one kernel)",
+                     "achieved": ax_gbs, "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": ax_gbs / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "algorithmic_bytes_per_launch": BYTES_AX_DIR * dof, "bytes_per_dof": BYTES_AX_DIR,
+                     "bytes_per_dof_is": "p 8 + r 8 + dinv 8 + six G 48 + p written 8 + Ap written 8",
+                     "avg_ms": ax_ms, "avg_ms_is": "per CG iteration", "launches_timed": kern["ax"][1],
                      "share_of_step": kern["ax"][0] / ms_total, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
-        "kernels": {"ax": kernel_entry("ax", BYTES_AX), "gs": kernel_entry("gs", BYTES_GS),
-                    "update": kernel_entry("update", BYTES_UPDATE_PCG), "direction": kernel_entry("direction", BYTES_DIR_PCG)},
+        "kernels": {"ax": kernel_entry("ax", BYTES_AX_DIR, "direction update + Ax + mask + pAp"),
+                    "gs": kernel_entry("gs", bytes_gs_long, "in-place gather-scatter of the segments with more than two copies"),
+                    "update": kernel_entry("update", BYTES_UPDATE + 4.0, "x, r update + pairwise gather-scatter (4-byte link) + r.z + scalar step")},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * int(dof_all), "d2h_bytes_per_step": 8 * int(dof_all),
-                "ms_per_step": e_s / args.steps * 1e3, "api": "sempy_b200.elliptic.elliptic_pcg(mesh, b_host) -> x_host"},
+                "ms_per_step": e_s / args.steps * 1e3,
+                "api": "x, niter = sempy_b200.elliptic.elliptic_pcg(mesh, b) with a pageable NumPy b and a fresh NumPy x "
+                       "(the reference's calling convention)",
+                "with_pinned_buffers": {"value": e2e_pinned, "ms_per_step": p_s / args.steps * 1e3,
+                                        "api": "elliptic_pcg(mesh, b_pinned, out=x_pinned)"}},
         "gpu_launches": int(launches),
+        "check": check,
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
+    if cpu_ref is not None:
+        line["cpu_baseline_reference"] = cpu_ref
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -433,15 +627,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2)")
+    ap.add_argument("--nel", type=int, default=32, help="elements per side per GPU (default: BASELINE config 2; config 5: 48)")
     ap.add_argument("--perturb", type=float, default=0.0, help="vertex displacement in units of h (0.3 = the deformed mesh of config 4)")
     ap.add_argument("--strong", type=int, default=0, help="strong scaling: one box of STRONG^3 elements split over all GPUs (config 4: 64)")
-    ap.add_argument("--order", type=int, default=7, help="polynomial order N (BASELINE config 3: --order 15 --nel 16 or 32)")
+    ap.add_argument("--order", type=int, default=7, help="polynomial order N (BASELINE config 3: --order 15 --nel 32)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the small N-rank solve against the CPU oracle")
     args = ap.parse_args()
-    global N_ORDER, NQ, F_SHARED, BYTES_GS
-    N_ORDER, NQ = args.order, args.order + 1
-    F_SHARED = 1.0 - ((N_ORDER - 1) / (N_ORDER + 1)) ** 3
-    BYTES_GS = 20.0 * F_SHARED
+    global N_ORDER
+    N_ORDER = args.order
     if args.impl == "reference":
         run_reference(args)
     else:

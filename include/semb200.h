@@ -70,11 +70,18 @@ int semb_set_geom(semb_ctx* ctx, const double* G, int layout, int mem);
  * 479-480): local indices sorted by global id and the nglobal+1 segment
  * offsets (HOST or DEVICE arrays, `mem`).  Replaces gslib's GS.setup
  * (mesh.py:437-438); the schedule (segments with more than one copy, grouped by
- * length, copies in ascending local index, plus the per-node links of the pull
- * form) is built on the device.  Also builds rmult = 1/multiplicity
+ * length, copies in ascending local index, plus the partner links of the two-copy
+ * segments) is built on the device.  Also builds rmult = 1/multiplicity
  * (mesh.py:440-442). */
 int semb_set_gather_scatter(semb_ctx* ctx, const int64_t* global_to_local, const int64_t* global_start,
                             int64_t nglobal, int mem);
+/* The reference's gslib handle on its own (sempy/mesh.py:437-438: gs = GS(0);
+ * gs.setup(global_id int32, 1-based)): semb_gs_create makes a context that only
+ * gather-scatters vectors of n entries (semb_gs, semb_get_rmult); semb_gs_setup
+ * groups the ids on the device -- equal positive ids are copies of one node, id 0
+ * takes no part -- and builds the same schedule as semb_set_gather_scatter. */
+int semb_gs_create(semb_ctx** ctx, int device, int64_t n);
+int semb_gs_setup(semb_ctx* ctx, const int32_t* ids, int mem);
 /* Dirichlet nodes = Mesh.get_mask_ids() (sempy/mesh.py:482-485), HOST ids. */
 int semb_set_mask(semb_ctx* ctx, const int64_t* mask_ids, int64_t n_mask);
 /* Mesh.setup_mask on the device (sempy/mesh.py:449-477): a node is a Dirichlet
@@ -232,8 +239,9 @@ int64_t semb_launch_count(semb_ctx* ctx);
  * them.  "ax_l2_prefetch": 1 (default) / 0, bulk L2 prefetch of the geometric
  * factors in the tuned Ax kernels.  "p2p": 1 (default) / 0, peer-memory transport
  * vs NCCL for the halo exchange and the scalar all-reduces.  "gs_pull": 1 (default) / 0,
- * gather-scatter summed inside its consumer (CG update kernel, out-of-place pass of
- * semb_ax) vs the separate in-place pass. */
+ * inside semb_cg the two-copy segments of the gather-scatter are summed by the CG
+ * update kernel while it streams (only the longer segments keep an in-place pass)
+ * vs one in-place pass over all segments. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

@@ -50,8 +50,10 @@ class _GS:
         x[:] = sem_oracle.gather_scatter(x, self._order, self._start)
 
 
-def install(reference_root="/root/reference"):
-    """Make ``import sempy.mesh`` work against the reference checkout."""
+def install(reference_root="/root/reference", gslib=None):
+    """Make ``import sempy.mesh`` work against the reference checkout (or its copy oracle/_ref).
+    ``gslib``: a module to serve as ``gslib_wrapper`` instead of the NumPy stand-in (the GPU tests pass
+    ``sempy_b200.gslib_wrapper`` to run the unmodified reference mesh code on the CUDA gather-scatter)."""
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     meshio = types.ModuleType("meshio")
@@ -61,9 +63,14 @@ def install(reference_root="/root/reference"):
     gsw.GS = _GS
     gsw.gs_add = "gs_add"
     gsw.gs_double = "gs_double"
-    sys.modules["gslib_wrapper"] = gsw
+    sys.modules["gslib_wrapper"] = gslib if gslib is not None else gsw
     import sempy.kron
     import sempy.mesh
+
+    if gslib is not None:  # sempy.mesh may have been imported before with the stand-in
+        sempy.mesh.GS, sempy.mesh.gs_add, sempy.mesh.gs_double = gslib.GS, gslib.gs_add, gslib.gs_double
+    else:
+        sempy.mesh.GS, sempy.mesh.gs_add, sempy.mesh.gs_double = _GS, "gs_add", "gs_double"
 
     sempy.mesh.kron = functools.partial(sempy.kron.kron, order="C")
     return sempy

@@ -36,6 +36,8 @@ SIGNATURES = {
     "semb_set_derivative": (C.c_int, [C.c_void_p, C.c_void_p]),
     "semb_set_geom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "semb_set_gather_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "semb_gs_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64]),
+    "semb_gs_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "semb_set_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "semb_setup_mask_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "semb_get_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

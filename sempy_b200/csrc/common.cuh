@@ -144,10 +144,9 @@ struct semb_ctx {
   int64_t gs_var_nseg = 0;
   int64_t gs_var_off = 0;
   bool have_gs = false;
-  // pull form of the same schedule: link[q] = (len << 28) | offset of node q's segment in gs_ids, 0 for
-  // nodes without another local copy (and, once a halo is set, for nodes completed by the halo kernels)
+  // pull form of the two-copy segments: link[q] = 0x80000000 | the other copy's local index, 0 for every
+  // other node (and, once a halo is set, for nodes completed by the halo kernels)
   uint32_t* gs_link = nullptr;
-  bool pull_ok = false;  // every segment has <= 15 copies and the id table is shorter than 2^28
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 

@@ -20,7 +20,7 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 // Tuning knobs for A/B measurements (environment at load time, or semb_set_tuning at run time).
-// None of them changes results beyond rounding (gs_pull: the same fixed summation order as the push form).
+// None of them changes results (gs_pull: the same sums, a + b commutes bitwise).
 static int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
   return v ? atoi(v) : fallback;
@@ -29,8 +29,8 @@ static int env_int(const char* name, int fallback) {
 static int g_p2p_on = env_int("SEMB_P2P", 1);
 // "ax_l2_prefetch": 0 = no bulk L2 prefetch of G in the tuned Ax kernels
 static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
-// "gs_pull": 0 = separate in-place gather-scatter pass (push form) instead of summing the copies inside
-// the consumer (CG update kernel / out-of-place pull kernel)
+// "gs_pull": 0 = the whole gather-scatter as a separate in-place pass (push form) instead of summing the
+// two-copy segments inside the consumer (CG update kernel)
 static int g_gs_pull = env_int("SEMB_GS_PULL", 1);
 
 const NcclApi& nccl() {
@@ -146,11 +146,12 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 
 // ---- K2 dispatch -----------------------------------------------------------
 // in-place (push) form
-static int launch_gs(semb_ctx* c, double* x, const int* done) {
+// skip_pairs: the two-copy segments are left to the consumer (pull form, gs_pair)
+static int launch_gs(semb_ctx* c, double* x, const int* done, bool skip_pairs = false) {
   ProfScope ps(c, SEMB_K_GS);
   GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
-    if (k.len == 2) { plan.n2 = k.nseg; plan.off2 = k.off; }
+    if (k.len == 2) { if (!skip_pairs) { plan.n2 = k.nseg; plan.off2 = k.off; } }
     else if (k.len == 4) { plan.n4 = k.nseg; plan.off4 = k.off; }
     else if (k.len == 8) { plan.n8 = k.nseg; plan.off8 = k.off; }
   }
@@ -177,15 +178,7 @@ static int launch_gs(semb_ctx* c, double* x, const int* done) {
   }
   return 0;
 }
-// out-of-place (pull) form: out = dssum(in) over the local copies
-static int launch_gs_pull(semb_ctx* c, const double* in, double* out) {
-  ProfScope ps(c, SEMB_K_GS);
-  c->launch_count++;
-  gs_pull_kernel<<<vec_grid(c->n / 2 + 1), VEC_NT, 0, c->stream>>>(in, out, c->gs_link, c->gs_ids, c->n);
-  SEMB_CUDA(cudaGetLastError());
-  return 0;
-}
-static inline bool use_pull(const semb_ctx* c) { return c->pull_ok && g_gs_pull; }
+static inline bool use_pull(const semb_ctx* c) { return g_gs_pull != 0; }
 
 // ---- multi-GPU halo --------------------------------------------------------
 static inline bool use_p2p(const semb_ctx* c) { return c->p2p && g_p2p_on; }
@@ -302,7 +295,7 @@ static int reduce_partials(semb_ctx* c, int64_t n, int64_t stride, int nout, dou
 // partial sums, group sums and tickets of the grid reductions (reduce.cuh); the CG update kernel's own
 // ticket is the last entry
 static int ensure_partials(semb_ctx* c) {
-  const int64_t need = std::max<int64_t>(c->E, 2 * (int64_t)kNumSMs * 8) + 16;
+  const int64_t need = std::max<int64_t>(c->Nq >= 2 ? c->E : 0, 2 * (int64_t)kNumSMs * 8) + 16;
   if (c->partials_cap < need) {
     cudaFree(c->partials);
     cudaFree(c->partials2);
@@ -448,6 +441,30 @@ int semb_create(semb_ctx** out, int device, int64_t num_elems, int Nq) {
   SEMB_CUDA(cudaMemset(c->info, 0, 4 * sizeof(int)));
   if (ensure_partials(c)) return 1;
   SEMB_CUDA(cudaDeviceSynchronize());  // the memsets above ran on the default stream
+  *out = c;
+  return 0;
+}
+
+// gslib-style handle (GS(comm), sempy/mesh.py:437): a context that only gather-scatters vectors of n entries
+int semb_gs_create(semb_ctx** out, int device, int64_t n) {
+  SEMB_CHECK(out != nullptr, "semb_gs_create: out is NULL");
+  SEMB_CHECK(n > 0 && n < (int64_t)2147483647, "semb_gs_create: n must be in [1, 2^31)");
+  SEMB_CUDA(cudaSetDevice(device));
+  semb_ctx* c = new semb_ctx();
+  c->device = device;
+  c->E = n;
+  c->Nq = 1;
+  c->Np = 1;
+  c->n = n;
+  SEMB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  SEMB_CUDA(cudaMalloc(&c->scal, sizeof(CgScalars) + 8 * sizeof(double)));
+  SEMB_CUDA(cudaMemset(c->scal, 0, sizeof(CgScalars) + 8 * sizeof(double)));
+  SEMB_CUDA(cudaMallocHost(&c->h_pinned, 64));
+  SEMB_CUDA(cudaMalloc(&c->info, 4 * sizeof(int)));
+  SEMB_CUDA(cudaMemset(c->info, 0, 4 * sizeof(int)));
+  if (ensure_partials(c)) return 1;
+  SEMB_CUDA(cudaDeviceSynchronize());
   *out = c;
   return 0;
 }
@@ -680,9 +697,8 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   }
   const int64_t nids = align4(lay.off[3] + nvar_ids);
   SEMB_CHECK(nids < (int64_t)2147483647, "semb_set_gather_scatter: id table too long");
-  c->pull_ok = h_info[1] <= 15 && nids < ((int64_t)1 << 28);
 
-  // 3. ids (copies of a segment in ascending local index) and the per-node links of the pull form
+  // 3. ids (copies of a segment in ascending local index) and the pair links of the pull form
   cudaFree(c->gs_ids);
   cudaFree(c->gs_link);
   c->gs_ids = nullptr;
@@ -692,8 +708,7 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   SEMB_CUDA(cudaMalloc(&c->gs_link, sizeof(uint32_t) * (size_t)(n + 2)));
   SEMB_CUDA(cudaMemset(c->gs_link, 0, sizeof(uint32_t) * (size_t)(n + 2)));
   if (lay.b[4] > 0) {
-    seg_emit_kernel<<<vec_grid(lay.b[4]), VEC_NT>>>(sorted, d_g2l, d_gst, lay, c->gs_var_start, c->gs_ids, c->gs_link,
-                                                    c->pull_ok ? 1 : 0);
+    seg_emit_kernel<<<vec_grid(lay.b[4]), VEC_NT>>>(sorted, d_g2l, d_gst, lay, c->gs_var_start, c->gs_ids, c->gs_link);
     SEMB_CUDA(cudaGetLastError());
   }
   SEMB_CUDA(cudaDeviceSynchronize());  // tables complete before the context's (non-blocking) stream uses them
@@ -706,6 +721,49 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   c->gs_nids = nids;
   c->have_gs = true;
   return build_rmult(c);
+}
+
+// GS.setup(ids) of gslib as SemPy drives it (sempy/mesh.py:437-438): entries with the same positive id are
+// copies of one node; id 0 marks an entry that takes no part.  The ids are grouped on the device (stable
+// radix sort by id, segment starts where the id changes) and handed to semb_set_gather_scatter.
+int semb_gs_setup(semb_ctx* c, const int32_t* ids, int mem) {
+  SEMB_CHECK(c && ids, "semb_gs_setup: NULL argument");
+  SEMB_TRY(bind_device(c));
+  const int64_t n = c->n;
+  DevTmp t_ids, k0, k1, i0, i1, fl, st, cnt, tmp, info;
+  const int32_t* d_ids;
+  SEMB_TRY(dev_view(ids, mem, (size_t)n, t_ids, &d_ids));
+  SEMB_TRY(k0.alloc(4 * (size_t)n));
+  SEMB_TRY(k1.alloc(4 * (size_t)n));
+  SEMB_TRY(i0.alloc(8 * (size_t)n));
+  SEMB_TRY(i1.alloc(8 * (size_t)n));
+  SEMB_TRY(fl.alloc(4 * (size_t)n));
+  SEMB_TRY(st.alloc(8 * ((size_t)n + 1)));
+  SEMB_TRY(cnt.alloc(8));
+  SEMB_TRY(info.alloc(4 * sizeof(int)));
+  SEMB_CUDA(cudaMemset(info.p, 0, 4 * sizeof(int)));
+  const int grid = vec_grid(n);
+  id_keys_kernel<<<grid, VEC_NT>>>(d_ids, k0.as<unsigned int>(), n, info.as<int>());
+  iota_kernel<<<grid, VEC_NT>>>(i0.as<int64_t>(), n);
+  size_t sort_bytes = 0, sel_bytes = 0;
+  SEMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0.as<unsigned int>(), k1.as<unsigned int>(), i0.as<int64_t>(),
+                                            i1.as<int64_t>(), (int)n));
+  SEMB_CUDA(cub::DeviceSelect::Flagged(nullptr, sel_bytes, i0.as<int64_t>(), fl.as<int>(), st.as<int64_t>(), cnt.as<int64_t>(), (int)n));
+  size_t tb = std::max(sort_bytes, sel_bytes);
+  SEMB_TRY(tmp.alloc(tb));
+  SEMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.as<unsigned int>(), k1.as<unsigned int>(), i0.as<int64_t>(),
+                                            i1.as<int64_t>(), (int)n));
+  id_flags_kernel<<<grid, VEC_NT>>>(k1.as<unsigned int>(), fl.as<int>(), n);
+  iota_kernel<<<grid, VEC_NT>>>(i0.as<int64_t>(), n);  // sorted positions
+  SEMB_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, i0.as<int64_t>(), fl.as<int>(), st.as<int64_t>(), cnt.as<int64_t>(), (int)n));
+  SEMB_CUDA(cudaGetLastError());
+  int64_t ng = 0;
+  int h_info[4];
+  SEMB_CUDA(cudaMemcpy(&ng, cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SEMB_CUDA(cudaMemcpy(h_info, info.p, sizeof(h_info), cudaMemcpyDeviceToHost));
+  SEMB_CHECK(h_info[0] == 0, "semb_gs_setup: negative id");
+  SEMB_CUDA(cudaMemcpy(st.as<int64_t>() + ng, &n, sizeof(int64_t), cudaMemcpyHostToDevice));
+  return semb_set_gather_scatter(c, i1.as<int64_t>(), st.as<int64_t>(), ng, SEMB_DEVICE);
 }
 
 int semb_set_mask(semb_ctx* c, const int64_t* mask_ids, int64_t n_mask) {
@@ -803,22 +861,8 @@ int semb_ax(semb_ctx* c, const double* p, double* ap, int flags, int mem) {
   Staged in, out;
   SEMB_TRY(stage_in(c, p, mem, c->n, in, true, 0));
   SEMB_TRY(stage_in(c, ap, mem, c->n, out, false, 1));
-  if (gs && use_pull(c)) {
-    // operator into scratch, then ONE streaming pass that sums the copies of every shared node on the fly
-    SEMB_TRY(ensure_vec(c, 5));
-    double* raw = c->vec[5];
-    SEMB_TRY(launch_ax(c, in.dev, raw, mask, false, 0, 0, c->E, nullptr, nullptr, 0, 0, nullptr));
-    if (c->have_halo) {
-      c->seq_halo++;
-      SEMB_TRY(halo_gather(c, raw, c->stream, nullptr));
-      SEMB_TRY(halo_exchange(c, c->stream));
-    }
-    SEMB_TRY(launch_gs_pull(c, raw, out.dev));
-    if (c->have_halo) SEMB_TRY(halo_scatter(c, out.dev, c->stream, nullptr));
-  } else {
-    SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, 0, c->E, nullptr, nullptr, 0, 0, nullptr));
-    if (gs) SEMB_TRY(gs_full(c, out.dev, nullptr));
-  }
+  SEMB_TRY(launch_ax(c, in.dev, out.dev, mask, false, 0, 0, c->E, nullptr, nullptr, 0, 0, nullptr));
+  if (gs) SEMB_TRY(gs_full(c, out.dev, nullptr));
   SEMB_TRY(stage_out(c, ap, mem, c->n, out));
   return 0;
 }
@@ -1233,7 +1277,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         c->seq_halo++;
         SEMB_TRY(halo_gather(c, Ap, c->stream, done));
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done));
-        if (!pull) SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(launch_gs(c, Ap, done, pull));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done, &s->pAp, 1));
       } else if (c->have_halo) {
         // NCCL fallback: same order, the exchange on a second stream
@@ -1246,17 +1290,15 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(halo_exchange(c, c->comm_stream));
         SEMB_CUDA(cudaEventRecord(c->ev_exchanged, c->comm_stream));
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done));
-        if (!pull) {
-          SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
-          SEMB_TRY(launch_gs(c, Ap, done));
-        }
+        SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
+        SEMB_TRY(launch_gs(c, Ap, done, pull));
         // one communicator: its two NCCL operations must not overlap, so the all-reduce follows the exchange
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
         SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
       } else {
         SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, c->E, zsrc, dinv, 0, cta2, done));
-        if (!pull) SEMB_TRY(launch_gs(c, Ap, done));
+        SEMB_TRY(launch_gs(c, Ap, done, pull));
       }
       // x += alpha p; r -= alpha dssum(Ap); r.z; scalar step              (elliptic.py:56-71)
       {
@@ -1270,7 +1312,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         ll.nranks = 1;
         if (tail && p2p) ll = ll_args(c, ++c->seq_scalar);
 #define SEMB_UPDATE(J, P)                                                                                               \
-  cg_update_kernel<J, P><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, c->gs_link, c->gs_ids, s, n, \
+  cg_update_kernel<J, P><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, c->gs_link, s, n, \
                                                         c->partials, ticket, hist, ll)
         if (jac && pull) SEMB_UPDATE(true, true);
         else if (jac) SEMB_UPDATE(true, false);

@@ -48,6 +48,21 @@ __global__ void scatter_ids_kernel(const int64_t* __restrict__ order, const int*
     gid[order[q]] = idscan[q];  // inclusive scan of the start flags = 1-based id
 }
 
+// gslib-style set-up from ids (GS.setup, sempy/mesh.py:437-438): keys for the stable sort by id, and the
+// segment starts of the sorted order (a new segment where the id changes; id 0 = "not shared": every
+// such entry is its own segment, as in gslib)
+__global__ void id_keys_kernel(const int32_t* __restrict__ ids, unsigned int* __restrict__ keys, int64_t n, int* __restrict__ info) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[q];
+    if (id < 0) atomicOr(info, 1);
+    keys[q] = (unsigned int)id;
+  }
+}
+__global__ void id_flags_kernel(const unsigned int* __restrict__ sorted_keys, int* __restrict__ flag, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    flag[q] = (q == 0 || sorted_keys[q] != sorted_keys[q - 1] || sorted_keys[q] == 0u) ? 1 : 0;
+}
+
 // Geometric factors of one element per CTA: coordinates staged in shared memory, nine derivatives per
 // node with D from the parameter block, then the reference's formulas in the reference's order.
 __global__ void geom_factors_kernel(const double* __restrict__ xe, const double* __restrict__ ye,
@@ -164,10 +179,10 @@ struct SegLayout {
   int64_t off[4];   // start of each class in ids (multiples of 4 ints)
 };
 
-// writes the ids of every shared segment (ascending) and the link of each of its copies
+// writes the ids of every shared segment (ascending) and the pair links of the two-copy segments
 __global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t* __restrict__ g2l,
                                 const int64_t* __restrict__ gstart, const SegLayout lay, const int32_t* __restrict__ var_start,
-                                int32_t* __restrict__ ids, uint32_t* __restrict__ link, int link_ok) {
+                                int32_t* __restrict__ ids, uint32_t* __restrict__ link) {
   const int64_t total = lay.b[4];
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = vals[t];
@@ -186,9 +201,9 @@ __global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t*
       }
       out[pos] = id;
     }
-    if (link_ok && len <= 15) {
-      const uint32_t lk = ((uint32_t)len << 28) | (uint32_t)dst;
-      for (int c = 0; c < len; ++c) link[out[c]] = lk;
+    if (len == 2) {  // pair links of the pull form: each copy points at the other (GS_LINK_PAIR)
+      link[out[0]] = 0x80000000u | (uint32_t)out[1];
+      link[out[1]] = 0x80000000u | (uint32_t)out[0];
     }
   }
 }

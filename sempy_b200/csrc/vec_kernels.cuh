@@ -116,77 +116,21 @@ gs_var_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const int
 }
 
 // ---------------------------------------------------------------------------
-// Pull form of the same schedule.  link[q] = (len << 28) | offset of node q's segment in `ids` (0: the node
-// has no other local copy, or the halo kernels complete it).  The consumer of a gather-scattered vector
-// reads, for every shared node, the copies of its segment in ascending local index and adds them in that
-// order -- every copy computes the bitwise identical sum, nothing is written back, and the separate pass
-// over the vector (K2: 18 B of sector traffic per node at 48 % of the DRAM peak, profiles/r01_summary.md)
-// disappears.  Inside semb_cg the consumer is the update kernel (r -= alpha * dssum(Ap)), for
-// semb_ax(GS) an out-of-place streaming kernel.  The gathers hit L2: the copies of a node sit in
-// elements that are neighbours in the mesh, and every sector gathered is also read by the stream itself.
+// Pull form for the segments with exactly two copies (73 % of the shared nodes of a hex mesh at N = 7:
+// the face-interior nodes).  link[q] = 0x80000000 | local index of node q's only other copy, 0 otherwise
+// (no other copy, a longer segment, or a node that the halo kernels complete).  The consumer of a
+// gather-scattered vector adds the partner's value to its own while it streams through: one predicated
+// gather per node, no index table, no divergence; a + b is commutative in IEEE arithmetic, so both copies
+// get the bitwise identical sum, nothing is written back and the pass over the len-2 class of K2
+// disappears.  Longer segments (edges, vertices: 16 % of the nodes) keep the in-place push form, run
+// BEFORE the consumer on their own class only (gs_fixed_kernel with n2 = 0).  Inside semb_cg the consumer
+// is the update kernel (r -= alpha * dssum(Ap)).  The gathers hit L2: the partner sits in a
+// neighbouring element that the same pass streams through.
 // ---------------------------------------------------------------------------
-constexpr uint32_t GS_LINK_OFF_MASK = 0x0fffffffu;
+constexpr uint32_t GS_LINK_PAIR = 0x80000000u;
 
-__device__ __forceinline__ double gs_pull(const double* __restrict__ v, const int32_t* __restrict__ ids, uint32_t link,
-                                          int64_t q, double own) {
-  const int len = (int)(link >> 28);
-  const int32_t* p = ids + (link & GS_LINK_OFF_MASK);
-  if (len == 2) {
-    const int2 i2 = __ldg(reinterpret_cast<const int2*>(p));
-    const double a = i2.x == q ? own : v[i2.x];
-    const double b = i2.y == q ? own : v[i2.y];
-    return a + b;
-  }
-  if (len == 4) {
-    const int4 i4 = __ldg(reinterpret_cast<const int4*>(p));
-    const double a = i4.x == q ? own : v[i4.x];
-    const double b = i4.y == q ? own : v[i4.y];
-    const double c = i4.z == q ? own : v[i4.z];
-    const double d = i4.w == q ? own : v[i4.w];
-    return ((a + b) + c) + d;
-  }
-  if (len == 8) {
-    const int4 i4 = __ldg(reinterpret_cast<const int4*>(p));
-    const int4 j4 = __ldg(reinterpret_cast<const int4*>(p) + 1);
-    const double a = i4.x == q ? own : v[i4.x];
-    const double b = i4.y == q ? own : v[i4.y];
-    const double c = i4.z == q ? own : v[i4.z];
-    const double d = i4.w == q ? own : v[i4.w];
-    const double e = j4.x == q ? own : v[j4.x];
-    const double f = j4.y == q ? own : v[j4.y];
-    const double g = j4.z == q ? own : v[j4.z];
-    const double h = j4.w == q ? own : v[j4.w];
-    return ((((((a + b) + c) + d) + e) + f) + g) + h;
-  }
-  const int first = __ldg(p);
-  double s = first == q ? own : v[first];
-  for (int c = 1; c < len; ++c) {
-    const int id = __ldg(p + c);
-    s += id == q ? own : v[id];
-  }
-  return s;
-}
-
-// out = dssum(in), out of place (in != out), streaming.
-__global__ void __launch_bounds__(VEC_NT)
-gs_pull_kernel(const double* __restrict__ in, double* __restrict__ out, const uint32_t* __restrict__ link,
-               const int32_t* __restrict__ ids, int64_t n) {
-  const int64_t n2 = n >> 1;
-  const double2* in2 = reinterpret_cast<const double2*>(in);
-  const uint2* l2 = reinterpret_cast<const uint2*>(link);
-  double2* o2 = reinterpret_cast<double2*>(out);
-  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    double2 v = in2[q];
-    const uint2 lk = __ldg(l2 + q);
-    if (lk.x) v.x = gs_pull(in, ids, lk.x, 2 * q, v.x);
-    if (lk.y) v.y = gs_pull(in, ids, lk.y, 2 * q + 1, v.y);
-    o2[q] = v;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int64_t q = n - 1;
-    const uint32_t lk = link[q];
-    out[q] = lk ? gs_pull(in, ids, lk, q, in[q]) : in[q];
-  }
+__device__ __forceinline__ double gs_pair(const double* __restrict__ v, uint32_t link) {
+  return (link & GS_LINK_PAIR) ? v[link & ~GS_LINK_PAIR] : 0.0;
 }
 
 // link[copy] = 0 for the copies of interface nodes (their sum is completed by the halo kernels)
@@ -530,10 +474,10 @@ __device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* par
 
 // ---------------------------------------------------------------------------
 // K3: x += alpha p ; r -= alpha dssum(Ap) ; partial of sum rmult r r (or rmult r dinv r)
-// (sempy/elliptic.py:52-60; iterative.py:66-73).  With PULL the gather-scatter of Ap (elliptic.py:54)
-// happens here: Ap holds the UNSUMMED operator output and every shared node adds the copies of its
-// segment on the fly (gs_pull), so Ap is neither re-read by a separate pass nor written back.
-// 57 B per node with Jacobi (+4 link, +~2.3 ids with PULL).
+// (sempy/elliptic.py:52-60; iterative.py:66-73).  With PULL the pairwise part of the gather-scatter of Ap
+// (elliptic.py:54) happens here: nodes with exactly one other copy add the partner's UNSUMMED operator
+// output on the fly (gs_pair), so that part of Ap is neither re-read by a separate pass nor written back.
+// 57 B per node with Jacobi (+4 link with PULL, + the partner sectors from L2).
 // ---------------------------------------------------------------------------
 // The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node) and
 // turned back into the identical double through a small shared-memory table of 1.0/c (a division in
@@ -543,7 +487,7 @@ template <bool JACOBI, bool PULL>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                  const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
-                 const uint32_t* __restrict__ link, const int32_t* __restrict__ ids, CgScalars* __restrict__ s, int64_t n,
+                 const uint32_t* __restrict__ link, CgScalars* __restrict__ s, int64_t n,
                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ hist,
                  const LlArgs ll) {
   if (s->done) return;
@@ -561,15 +505,20 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
   const uint2* l2 = reinterpret_cast<const uint2*>(link);
   for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    const double2 pv = p2[q];
     double2 av = a2[q];
+    double2 pa = make_double2(0.0, 0.0);
     if (PULL) {
       const uint2 lk = __ldg(l2 + q);
-      if (lk.x) av.x = gs_pull(Ap, ids, lk.x, 2 * q, av.x);
-      if (lk.y) av.y = gs_pull(Ap, ids, lk.y, 2 * q + 1, av.y);
+      pa.x = gs_pair(Ap, lk.x);
+      pa.y = gs_pair(Ap, lk.y);
     }
+    const double2 pv = p2[q];
     const uchar2 mc = m2[q];
     double2 xv = x2[q], rv = r2[q];
+    if (PULL) {
+      av.x += pa.x;
+      av.y += pa.y;
+    }
     xv.x = xv.x + alpha * pv.x;
     xv.y = xv.y + alpha * pv.y;
     rv.x = rv.x - alpha * av.x;
@@ -589,7 +538,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t q = n - 1;
     double av = Ap[q];
-    if (PULL && link[q]) av = gs_pull(Ap, ids, link[q], q, av);
+    if (PULL) av += gs_pair(Ap, link[q]);
     const double xv = x[q] + alpha * p[q];
     const double rv = r[q] - alpha * av;
     x[q] = xv;

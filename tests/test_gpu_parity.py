@@ -374,3 +374,83 @@ def test_full_size_properties(big_mesh):
     xm = x.clone()
     m.apply_mask(xm)
     assert torch.equal(xm, x)
+
+
+def test_bitwise_repeatable_and_independent_of_the_gs_form():
+    """Every sum of the solver has a fixed order (no floating-point atomics): two solves give the same
+    bits, and so does the solve with the pairwise gather-scatter as a separate in-place pass
+    (gs_pull = 0) instead of inside the update kernel (a + b commutes exactly)."""
+    from sempy_b200 import _capi
+    from sempy_b200.elliptic import elliptic_cg, elliptic_pcg
+    from sempy_b200.mesh import box_mesh
+
+    m = box_mesh(6, 5, 4, perturb=0.3, seed=7)
+    m.find_physical_coordinates(7)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    rng = np.random.default_rng(2)
+    b = m.apply_mask(m.dssum(rng.standard_normal(m.get_num_elems() * m.Np)))
+    lib = _capi.lib()
+    runs = []
+    for pull in (1, 1, 0):
+        _capi.check(lib.semb_set_tuning(b"gs_pull", pull))
+        runs.append((elliptic_pcg(m, b, tol=1e-10, maxit=500), elliptic_cg(m, b, tol=1e-9, maxit=40)))
+    _capi.check(lib.semb_set_tuning(b"gs_pull", 1))
+    for (xp, itp), (xc, itc) in runs[1:]:
+        assert itp == runs[0][0][1] and itc == runs[0][1][1]
+        assert np.array_equal(xp, runs[0][0][0]) and np.array_equal(xc, runs[0][1][0])
+    x1 = m.dssum(b.copy())
+    x2 = m.dssum(b.copy())
+    assert np.array_equal(x1, x2)
+
+
+def test_gslib_handle():
+    """GS(0).setup(ids) / .gs(x, gs_double, gs_add) (sempy/mesh.py:437-445) on arbitrary ids, id 0 = not shared."""
+    torch = pytest.importorskip("torch")
+    from sempy_b200.gslib_wrapper import GS, gs_add, gs_double
+
+    rng = np.random.default_rng(8)
+    n = 50000
+    ids = rng.integers(0, 9000, n).astype(np.int32)  # multiplicities from 1 to ~15, some zeros
+    x = rng.standard_normal(n)
+    ref = x.copy()
+    for k in np.unique(ids[ids > 0]):
+        sel = ids == k
+        ref[sel] = x[sel].sum()
+    gs = GS(0)
+    gs.setup(ids)
+    y = x.copy()
+    assert gs.gs(y, gs_double, gs_add) is None
+    assert rel_inf(y, ref) < 1e-14 and np.array_equal(y[ids == 0], x[ids == 0])
+    t = torch.from_numpy(x).cuda()
+    gs.gs(t, gs_double, gs_add)
+    assert np.array_equal(t.cpu().numpy(), y)
+    with pytest.raises(ValueError):
+        gs.gs(x[:-1].copy(), gs_double, gs_add)
+
+
+def test_unmodified_reference_mesh_runs_on_the_cuda_gather_scatter():
+    """The reference's own sempy/mesh.py (verbatim copy under oracle/_ref, see oracle/make_ref.py) with
+    sempy_b200.gslib_wrapper in place of gslib: numbering, rmult and dssum as in the golden fixtures."""
+    from oracle import make_ref, ref_stubs
+
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    import sempy_b200.gslib_wrapper as gsw
+
+    ref_stubs.install(make_ref.DEST, gslib=gsw)
+    try:
+        from sempy.mesh import load_mesh as ref_load_mesh
+
+        g = load_golden("box008_N7")
+        mesh = ref_load_mesh("box008.msh")
+        mesh.find_physical_coordinates(7)
+        mesh.establish_global_numbering()
+        assert isinstance(mesh.gs, gsw.GS)
+        assert np.array_equal(mesh.global_id, g["global_id"]) and np.array_equal(mesh.get_rmult(), g["rmult"])
+        x = g["p"].copy()
+        assert mesh.dssum(x) is x
+        assert rel_inf(x * mesh.get_rmult(), g["p_cont"]) < 1e-15
+    finally:
+        ref_stubs.install(make_ref.DEST)
