@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 N_ORDER = 7
 TOL = 1e-8
+MAXIT = 10000  # as the reference driver (poisson.py:42)
 CPU_ITERS = 10  # PCG iterations per CPU step: a bounded sample of the ~45-iteration solve
 
 
@@ -393,7 +394,7 @@ def run_ours(args):
     p2p_on = world > 1 and os.environ.get("SEMB_P2P", "1") != "0"
 
     def solve_dev():
-        return elliptic_pcg(mesh, b_dev, tol=TOL, maxit=1000)
+        return elliptic_pcg(mesh, b_dev, tol=TOL, maxit=MAXIT)
 
     # ---- device-resident arm -------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -477,12 +478,12 @@ def run_ours(args):
     # (a) the drop-in call exactly as the reference's callers make it: a pageable NumPy b, a fresh NumPy x
     b_host = b_dev.cpu().numpy()
     for _ in range(2):
-        x_host, _ = elliptic_pcg(mesh, b_host, tol=TOL, maxit=1000)
+        x_host, _ = elliptic_pcg(mesh, b_host, tol=TOL, maxit=MAXIT)
     sync_all()
     t0 = time.perf_counter()
     e_iters = 0
     for _ in range(args.steps):
-        x_host, it = elliptic_pcg(mesh, b_host, tol=TOL, maxit=1000)
+        x_host, it = elliptic_pcg(mesh, b_host, tol=TOL, maxit=MAXIT)
         e_iters += it
     sync_all()
     e_s = over_ranks(time.perf_counter() - t0, "MAX")
@@ -494,12 +495,12 @@ def run_ours(args):
     x_pin = torch.empty(dof, dtype=torch.float64).pin_memory()
     b_pin_np, x_pin_np = b_pin.numpy(), x_pin.numpy()
     for _ in range(2):
-        elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
+        elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=MAXIT, out=x_pin_np)
     sync_all()
     t0 = time.perf_counter()
     p_iters = 0
     for _ in range(args.steps):
-        _, it = elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=1000, out=x_pin_np)
+        _, it = elliptic_pcg(mesh, b_pin_np, tol=TOL, maxit=MAXIT, out=x_pin_np)
         p_iters += it
     sync_all()
     p_s = over_ranks(time.perf_counter() - t0, "MAX")

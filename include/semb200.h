@@ -223,6 +223,11 @@ int semb_p2p_attach(semb_ctx* ctx, const char* handles, const int64_t* peer_recv
 int semb_malloc(int device, void** ptr, int64_t bytes);
 int semb_free(int device, void* ptr);
 int semb_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind /*0 h2d, 1 d2h, 2 d2d*/);
+/* Pinned host memory for result vectors (device -> host by direct DMA).  HOST
+ * arguments in pageable memory are also accepted everywhere: they are staged
+ * through a ring of pinned chunks by a few host threads. */
+int semb_host_alloc(void** ptr, int64_t bytes);
+int semb_host_free(void* ptr);
 
 /* ---- measurement --------------------------------------------------------
  * With profiling on, every launch of the named kernels is bracketed by CUDA

@@ -525,6 +525,105 @@ def elliptic_pcg_jacobi(ax, dinv, mask, g2l, gstart, rmult, b, tol=1e-8, maxit=1
 
 
 # --------------------------------------------------------------------------
+# Fast-diagonalisation preconditioner: the reference's single-element sketch
+# (example.py:71-114 fdm_d_inv, :155-171 fast_kron, :186-190 precon_fdm) applied
+# element by element to the INTERIOR nodes, point Jacobi on the element surfaces.
+# --------------------------------------------------------------------------
+
+
+def fdm_1d(N):
+    """example.py:71-100 with the restriction R dropping both end nodes: Ah = Dh^T Bh Dh symmetrised,
+    generalised eigenproblem of the restricted pair (scipy.linalg.eigh(A, B) as the reference calls it)."""
+    import scipy.linalg as sla
+
+    _, w = gauss_lobatto(N)
+    Bh = np.diag(w)
+    Dh = reference_derivative_matrix(N)
+    Ah = Dh.T @ Bh @ Dh
+    Ah = 0.5 * (Ah + Ah.T)
+    I = np.identity(N + 1)
+    R = I[1:-1, :]
+    A, B = R @ Ah @ R.T, R @ Bh @ R.T
+    L, S = sla.eigh(A, B)
+    return S.real, L.real
+
+
+def fast_kron(Sz, Sy, Sx, U):
+    """example.py:155-171."""
+    nx, mx = Sx.shape
+    ny, my = Sy.shape
+    nz, mz = Sz.shape
+    U = U.reshape((my * mz, mx))
+    U = np.dot(U, Sx.T)
+    U = U.reshape((mz, my, nx))
+    V = np.zeros((mz, ny, nx))
+    for i in range(mz):
+        V[i, :, :] = np.dot(Sy, U[i, :, :])
+    V = V.reshape((mz, nx * ny))
+    U = np.dot(Sz, V)
+    return U.reshape((nx * ny * nz,))
+
+
+def fdm_element_scales(vx, vy, vz):
+    """a_r, a_s, a_t = (2/L)^2 and 8/(L_r L_s L_t) per element, L = mean edge length per local direction
+    (vertices in gmsh order, sempy/mesh.py:272-274 gives the lexicographic permutation)."""
+    lex = [0, 1, 3, 2, 4, 5, 7, 6]
+    out = np.zeros((vx.shape[0], 4))
+    for e in range(vx.shape[0]):
+        v = np.stack([vx[e, lex], vy[e, lex], vz[e, lex]], axis=1)  # [k*4 + j*2 + i]
+        L = []
+        for stride in (1, 2, 4):
+            starts = [q for q in range(8) if not (q // stride) % 2]
+            L.append(np.mean([np.linalg.norm(v[q + stride] - v[q]) for q in starts]))
+        out[e] = [(2 / L[0]) ** 2, (2 / L[1]) ** 2, (2 / L[2]) ** 2, 8.0 / (L[0] * L[1] * L[2])]
+    return out
+
+
+def fdm_apply(r, N, S, lam, esc, dinv):
+    """z = M^-1 r: example.py:186-190 (R, S^T(x)S^T(x)S^T, dinv, S(x)S(x)S, R^T) on each element's interior,
+    z = dinv * r on its surface."""
+    n = N + 1
+    E = esc.shape[0]
+    r3 = r.reshape(E, n, n, n)
+    z = (dinv * r).reshape(E, n, n, n).copy()
+    if n > 2:
+        m = n - 2
+        for e in range(E):
+            ax, ay, az, sc = esc[e]
+            d = sc / (ax * lam[None, None, :] + ay * lam[None, :, None] + az * lam[:, None, None])
+            ri = np.ascontiguousarray(r3[e, 1:-1, 1:-1, 1:-1]).reshape(-1)
+            bb = fast_kron(S.T, S.T, S.T, ri) * d.reshape(-1)
+            z[e, 1:-1, 1:-1, 1:-1] = fast_kron(S, S, S, bb).reshape(m, m, m)
+    return z.reshape(-1)
+
+
+def elliptic_pcg_fdm(ax, minv, mask, g2l, gstart, rmult, b, tol=1e-8, maxit=100):
+    """sempy/iterative.py:45-85 on local vectors (as elliptic_pcg_jacobi) with z = minv(r)."""
+    norm_b = np.dot(rmult * b, b)
+    TOL = max(tol * tol * norm_b, tol * tol)
+    x = np.zeros(b.size)
+    r = b
+    niter = 0
+    z = minv(r)
+    rdotz = np.dot(rmult * r, z)
+    p = z
+    while niter < maxit and rdotz > TOL:
+        Ap = ax(p) * mask
+        pAp = np.dot(Ap, p)
+        alpha = rdotz / pAp
+        Ap = gather_scatter(Ap, g2l, gstart)
+        x = x + alpha * p
+        r = r - alpha * Ap
+        z = minv(r)
+        rdotz0 = rdotz
+        rdotz = np.dot(rmult * r, z)
+        beta = rdotz / rdotz0
+        p = z + beta * p
+        niter += 1
+    return x, niter
+
+
+# --------------------------------------------------------------------------
 # Synthetic meshes shared by tests and bench (not in the reference)
 # --------------------------------------------------------------------------
 

@@ -89,6 +89,8 @@ SIGNATURES = {
     "semb_malloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int64]),
     "semb_free": (C.c_int, [C.c_int, C.c_void_p]),
     "semb_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "semb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "semb_host_free": (C.c_int, [C.c_void_p]),
     "semb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "semb_profile_reset": (C.c_int, [C.c_void_p]),
     "semb_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -196,3 +198,46 @@ class DevBuf:
                 self.ptr = None
         except Exception:
             pass
+
+
+class _PinnedPool:
+    """Result vectors in pinned host memory.  ``empty(n)`` returns a fresh float64 ndarray whose memory
+    comes from cudaMallocHost (the device -> host copy of a result is then one direct DMA, ~2.5x faster
+    than into pageable memory); when the array (and every view of it) has been garbage collected the
+    block goes back to the pool, so a solve loop allocates once.  At most ``keep`` idle blocks are kept."""
+
+    def __init__(self, keep=4):
+        self.keep = keep
+        self.idle = {}  # nbytes -> [address]
+
+    def empty(self, n):
+        import weakref
+
+        nbytes = max(int(n) * 8, 8)
+        free = self.idle.get(nbytes)
+        if free:
+            addr = free.pop()
+        else:
+            handle = C.c_void_p()
+            check(lib().semb_host_alloc(C.byref(handle), nbytes))
+            addr = handle.value
+        buf = (C.c_double * int(n)).from_address(addr)
+        weakref.finalize(buf, self._release, addr, nbytes)
+        return np.frombuffer(buf, dtype=np.float64, count=int(n))
+
+    def _release(self, addr, nbytes):
+        try:
+            free = self.idle.setdefault(nbytes, [])
+            if sum(len(v) for v in self.idle.values()) < self.keep:
+                free.append(addr)
+            else:
+                lib().semb_host_free(addr)
+        except Exception:
+            pass
+
+
+_pinned = _PinnedPool()
+
+
+def pinned_empty(n):
+    return _pinned.empty(n)

@@ -15,5 +15,5 @@ for src in semb200 k1_ax8 k1_axl_lo k1_axl_hi k1_generic; do
 done
 for pid in "${pids[@]}"; do wait "$pid"; done
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/semb200.o "$OBJ"/k1_ax8.o "$OBJ"/k1_axl_lo.o \
-  "$OBJ"/k1_axl_hi.o "$OBJ"/k1_generic.o -ldl
+  "$OBJ"/k1_axl_hi.o "$OBJ"/k1_generic.o -ldl -lpthread
 echo "built $OUT"

@@ -111,6 +111,19 @@ struct HaloPeers {
   int64_t peer_off[LL_MAXR];  // start of my block in that neighbour's halo part (entries)
 };
 
+// Pageable host memory <-> device through a ring of pinned chunks filled / drained by a few host threads
+// (a plain cudaMemcpy from pageable memory stages through ONE driver thread at ~7 GB/s, measured 37 ms
+// for the 2 x 134 MB of a 32^3-element solve; the ring overlaps several memcpy threads with the DMA).
+constexpr int HS_THREADS = 4;
+constexpr size_t HS_CHUNK = (size_t)4 << 20;  // bytes per chunk
+struct HostStager {
+  bool ready = false;
+  cudaStream_t stream[HS_THREADS] = {};
+  char* slot[HS_THREADS][2] = {};
+  cudaEvent_t ev[HS_THREADS][2] = {};
+  cudaEvent_t fence = nullptr;
+};
+
 struct Profile {
   bool on = false;
   int mask = 0xffff;
@@ -166,6 +179,7 @@ struct semb_ctx {
   int64_t hist_cap = 0;
   double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,scratch
   double* stage[2] = {nullptr, nullptr};  // pooled staging of HOST vector arguments (never freed per call)
+  semb::HostStager hs;                    // pinned ring for pageable HOST arguments
   int* h_pinned = nullptr;  // pinned {done, niter}
 
   // multi-GPU: NCCL communicator, interface ("halo") tables of this rank's element slab

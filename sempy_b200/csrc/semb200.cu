@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <utility>
 
 #include "aux_kernels.cuh"
@@ -311,6 +312,114 @@ static int ensure_partials(semb_ctx* c) {
   return 0;
 }
 
+// ---- host <-> device copies of caller vectors -------------------------------------------------
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+static int hs_init(semb_ctx* c) {
+  HostStager& h = c->hs;
+  if (h.ready) return 0;
+  for (int t = 0; t < HS_THREADS; ++t) {
+    SEMB_CUDA(cudaStreamCreateWithFlags(&h.stream[t], cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+      SEMB_CUDA(cudaMallocHost(&h.slot[t][q], HS_CHUNK));
+      SEMB_CUDA(cudaEventCreateWithFlags(&h.ev[t][q], cudaEventDisableTiming));
+    }
+  }
+  SEMB_CUDA(cudaEventCreateWithFlags(&h.fence, cudaEventDisableTiming));
+  h.ready = true;
+  return 0;
+}
+static void hs_free(semb_ctx* c) {
+  HostStager& h = c->hs;
+  if (!h.ready) return;
+  for (int t = 0; t < HS_THREADS; ++t) {
+    for (int q = 0; q < 2; ++q) {
+      cudaFreeHost(h.slot[t][q]);
+      cudaEventDestroy(h.ev[t][q]);
+    }
+    cudaStreamDestroy(h.stream[t]);
+  }
+  cudaEventDestroy(h.fence);
+  h.ready = false;
+}
+// Copy `bytes` between pageable host memory and the device, ordered after the work already queued on
+// c->stream; returns when the data has arrived (host side: complete; device side: c->stream waits for it).
+static int hs_copy(semb_ctx* c, void* dev, void* host, size_t bytes, bool to_device) {
+  if (bytes < 2 * HS_CHUNK || host_is_pinned(host)) {
+    if (to_device) SEMB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    else {
+      SEMB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+      SEMB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+  }
+  SEMB_TRY(hs_init(c));
+  HostStager& h = c->hs;
+  SEMB_CUDA(cudaEventRecord(h.fence, c->stream));
+  const size_t nchunk = (bytes + HS_CHUNK - 1) / HS_CHUNK;
+  cudaError_t errs[HS_THREADS];
+  std::thread workers[HS_THREADS];
+  for (int t = 0; t < HS_THREADS; ++t) {
+    errs[t] = cudaSuccess;
+    workers[t] = std::thread([&, t]() {
+      cudaError_t e = cudaSetDevice(c->device);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(h.stream[t], h.fence, 0);
+      auto span = [&](size_t ch, size_t& off, size_t& len) {
+        off = ch * HS_CHUNK;
+        len = std::min(HS_CHUNK, bytes - off);
+      };
+      size_t off, len;
+      if (to_device) {
+        int use = 0;
+        for (size_t ch = t; ch < nchunk && e == cudaSuccess; ch += HS_THREADS, ++use) {
+          const int q = use & 1;
+          if (use >= 2) e = cudaEventSynchronize(h.ev[t][q]);  // the DMA out of this slot has finished
+          if (e != cudaSuccess) break;
+          span(ch, off, len);
+          std::memcpy(h.slot[t][q], static_cast<char*>(host) + off, len);
+          e = cudaMemcpyAsync(static_cast<char*>(dev) + off, h.slot[t][q], len, cudaMemcpyHostToDevice, h.stream[t]);
+          if (e == cudaSuccess) e = cudaEventRecord(h.ev[t][q], h.stream[t]);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h.stream[t]);
+      } else {
+        // DMA of chunk k+1 into the other slot runs while chunk k is copied out
+        size_t ch = t;
+        int use = 0;
+        if (ch < nchunk) {
+          span(ch, off, len);
+          e = cudaMemcpyAsync(h.slot[t][0], static_cast<char*>(dev) + off, len, cudaMemcpyDeviceToHost, h.stream[t]);
+          if (e == cudaSuccess) e = cudaEventRecord(h.ev[t][0], h.stream[t]);
+        }
+        for (; ch < nchunk && e == cudaSuccess; ch += HS_THREADS, ++use) {
+          const int q = use & 1;
+          const size_t nxt = ch + HS_THREADS;
+          if (nxt < nchunk) {
+            size_t o2, l2;
+            span(nxt, o2, l2);
+            e = cudaMemcpyAsync(h.slot[t][q ^ 1], static_cast<char*>(dev) + o2, l2, cudaMemcpyDeviceToHost, h.stream[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(h.ev[t][q ^ 1], h.stream[t]);
+            if (e != cudaSuccess) break;
+          }
+          e = cudaEventSynchronize(h.ev[t][q]);
+          if (e != cudaSuccess) break;
+          span(ch, off, len);
+          std::memcpy(static_cast<char*>(host) + off, h.slot[t][q], len);
+        }
+      }
+      errs[t] = e;
+    });
+  }
+  for (int t = 0; t < HS_THREADS; ++t) workers[t].join();
+  for (int t = 0; t < HS_THREADS; ++t) SEMB_CUDA(errs[t]);
+  return 0;
+}
+
 // Host <-> device staging of caller vectors through two pooled buffers of the context (allocated on
 // first use, kept): a reference-style loop that calls mesh.dssum(x) with NumPy arrays pays two copies per
 // call, not an allocation.
@@ -325,12 +434,12 @@ static int stage_in(semb_ctx* c, const double* src, int mem, int64_t n, Staged& 
   }
   if (c->stage[slot] == nullptr) SEMB_CUDA(cudaMalloc(&c->stage[slot], sizeof(double) * (size_t)std::max<int64_t>(c->n, 2)));
   s.dev = c->stage[slot];
-  if (copy) SEMB_CUDA(cudaMemcpyAsync(s.dev, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  if (copy) SEMB_TRY(hs_copy(c, s.dev, const_cast<double*>(src), sizeof(double) * (size_t)n, true));
   return 0;
 }
 static int stage_out(semb_ctx* c, double* dst, int mem, int64_t n, Staged& s) {
   if (mem == SEMB_DEVICE) return 0;
-  SEMB_CUDA(cudaMemcpyAsync(dst, s.dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  SEMB_TRY(hs_copy(c, s.dev, dst, sizeof(double) * (size_t)n, false));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   return check_ll_error(c);
 }
@@ -490,6 +599,7 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->fdm_invL);
   for (double* v : c->vec) cudaFree(v);
   for (double* v : c->stage) cudaFree(v);
+  hs_free(c);
   cudaFreeHost(c->h_pinned);
   for (int k = 0; k < SEMB_K_COUNT; ++k) {
     for (cudaEvent_t e : c->prof.start[k]) cudaEventDestroy(e);
@@ -1343,8 +1453,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   *niter = c->h_pinned[0];
   if (history != nullptr && *niter > 0)
     SEMB_CUDA(cudaMemcpyAsync(history, c->hist, sizeof(double) * 5 * (size_t)(*niter), cudaMemcpyDeviceToHost, c->stream));
-  if (mem == SEMB_HOST)
-    SEMB_CUDA(cudaMemcpyAsync(x, xdev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (mem == SEMB_HOST) SEMB_TRY(hs_copy(c, xdev, x, sizeof(double) * (size_t)n, false));
   SEMB_CUDA(cudaStreamSynchronize(c->stream));
   return check_ll_error(c);
 }
@@ -1583,6 +1692,16 @@ int semb_malloc(int device, void** ptr, int64_t bytes) {
 int semb_free(int device, void* ptr) {
   SEMB_CUDA(cudaSetDevice(device));
   SEMB_CUDA(cudaFree(ptr));
+  return 0;
+}
+// pinned (page-locked) host memory: results allocated here come back from the device by direct DMA
+int semb_host_alloc(void** ptr, int64_t bytes) {
+  SEMB_CHECK(ptr && bytes >= 0, "semb_host_alloc: bad argument");
+  SEMB_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return 0;
+}
+int semb_host_free(void* ptr) {
+  SEMB_CUDA(cudaFreeHost(ptr));
   return 0;
 }
 int semb_memcpy(int device, void* dst, const void* src, int64_t bytes, int kind) {

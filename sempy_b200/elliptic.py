@@ -34,7 +34,8 @@ def _new_like(mesh, x, name):
     xin = _capi.as_f64(np.asarray(x)).reshape(-1)
     if xin.size != size:
         raise ValueError(f"{name}: expected {size} entries, got {xin.size}")
-    return xin, np.empty_like(xin), _capi.HOST
+    # the result lives in pinned host memory (direct DMA from the device); to the caller it is a fresh ndarray
+    return xin, _capi.pinned_empty(xin.size), _capi.HOST
 
 
 def _ax(mesh, p, flags):
@@ -53,6 +54,10 @@ def elliptic_ax(mesh, p):
 
 def _cg(mesh, b, tol, maxit, verbose, precond, out=None):
     ctx = mesh._context(need=("D", "geom", "gs"))  # the mask is optional: applied when setup_mask() has run
+    if precond == _capi.PRECOND_FDM:
+        from sempy_b200.fdm import setup_fdm
+
+        setup_fdm(mesh)
     bin_, x, mem = _new_like(mesh, b, "elliptic_cg")
     if out is not None:
         # caller-provided result buffer (e.g. pinned host memory); same kind as b
@@ -90,6 +95,12 @@ def elliptic_pcg(mesh, b, tol=1e-8, maxit=100, verbose=0, out=None):
     """Jacobi-preconditioned CG on local vectors: sempy/iterative.py:45-85 with
     Minv = mask / dssum(diag A), dots weighted by rmult as in elliptic_cg."""
     return _cg(mesh, b, tol, maxit, verbose, _capi.PRECOND_JACOBI, out)
+
+
+def elliptic_pcg_fdm(mesh, b, tol=1e-8, maxit=100, verbose=0, out=None):
+    """PCG with the fast-diagonalisation preconditioner (sempy_b200/fdm.py; the reference's sketch is
+    example.py:71-114,155-171,186-190): exact solves on the element interiors, Jacobi on the element surfaces."""
+    return _cg(mesh, b, tol, maxit, verbose, _capi.PRECOND_FDM, out)
 
 
 def elliptic_cg_loopy(mesh, b, tol=1e-12, maxit=100, verbose=0):

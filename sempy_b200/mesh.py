@@ -349,6 +349,7 @@ class Mesh:
         ctx = self._context(need=())
         _capi.check(ctx.lib.semb_set_geom(ctx.handle, g6.ctypes.data, _capi.G6, _capi.HOST))
         ctx.have.add("geom")
+        ctx.fdm_ready = False
         self._geom6_host = g6
 
     @property
@@ -444,6 +445,7 @@ class Mesh:
                                                 self._coords[2].ptr, jac.ptr, _capi.DEVICE))
             self._jaco = _NodeArray(dev=jac)
             ctx.have.add("geom")
+            ctx.fdm_ready = False
             return
         xr, xs, xt = gradient(self.xe, n, D)
         yr, ys, yt = gradient(self.ye, n, D)
