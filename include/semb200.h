@@ -174,7 +174,11 @@ int semb_set_fdm(semb_ctx* ctx, const double* S, const double* lambda, const dou
 /* cg(A,b,...) / pcg(A,Minv,b,...) of sempy/iterative.py:4-42,45-85 for any
  * operator: the vector updates and dots run on the device, A and Minv are
  * callbacks that receive DEVICE pointers (n doubles in, n doubles out) and
- * return 0 on success.  Minv = NULL selects cg. */
+ * return 0 on success.  Minv = NULL selects cg.  Synchronisation contract: the
+ * loop's own kernels run on the legacy default stream and the device is idle
+ * (cudaDeviceSynchronize) when a callback is entered; a callback may use any
+ * stream but must have its result complete in d_out when it returns (e.g. end
+ * with semb_synchronize on the context it used). */
 typedef int (*semb_apply_fn)(void* user, const double* d_in, double* d_out, int64_t n);
 int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_apply_fn Minv, void* Minv_user,
                     const double* b, double* x, double tol, int maxit, int mem, int* niter, double* history);

@@ -1,14 +1,25 @@
 // K1 for the higher orders (Nq = 9 ... 16, i.e. N = 8 ... 15): the same three-layout, contract-in-registers
-// design as ax8_kernel, with one CTA of Nq^2 threads per element and one line per thread.
+// design as ax8_kernel, with one CTA of Nq^2 threads per element and one line per thread and layout.
 //
-//   T: thread (i, j) owns the k-column           -> t-derivative and D^T_t in registers, G applied here
+//   T: thread (i, j) owns the k-column           -> t-derivative / D^T_t in registers, G applied here
 //   R: thread (j, k) owns the r-line (Nq contiguous values)
 //   S: thread (i, k) owns the s-line (stride = one padded row)
-// The element (two staged arrays of Nq planes) lives in shared memory: 74 KB at Nq = 16, so two CTAs
-// (16 warps) per SM -- the "shared-memory pressure" of BASELINE config 3.  Row padding makes the
-// R-line accesses conflict-free (RS/2 odd for even Nq -> LDS.128; RS odd for odd Nq -> LDS.64); S and
-// T accesses are contiguous across lanes.  D is replicated per phase in the parameter block (10 KB at
-// Nq = 16; see line8x2 in ax_kernels.cuh for why) and read through uniform registers.
+// The element lives in shared memory as THREE staged arrays of Nq planes (110 KB at Nq = 16, two CTAs =
+// 16 warps per SM -- the "shared-memory pressure" of BASELINE config 3):
+//   P1  u -> registers (T columns) and A                                  (+ the folded direction update)
+//   P2  r-line of A -> C (u_r) and s-line of A -> B (u_s) in ONE pass: both lines use the same entry of D
+//       for the same output index, so every D operand fetched (LDCU -> uniform register) feeds two DFMAs
+//   P3  u_t = D_t u in registers; per plane: G, (w_r, w_s, w_t) -> (A, B, C) at the thread's own T location;
+//       p.Ap accumulated as (grad u)^T G (grad u) = u_r w_r + u_s w_s + u_t w_t (no u needed later)
+//   P4  D^T along r (A, in place) and along s (B, in place) in one pass sharing D again; D^T along t from
+//       C into registers
+//   P5  sum, mask, store
+// Compared with accumulating D^T_t inside P3 and keeping u for the dot product (round 1: 128 registers
+// and 240 ... 1048 B of spills per thread with the CG variants, 6 barriers), nothing is live across a
+// phase but the u column in P1-P3 and the t-result in P4-P5: no spills, 4 barriers.
+// Row padding makes the R-line accesses conflict-free (RS/2 odd for even Nq -> LDS.128; RS odd for odd
+// Nq -> LDS.64); S and T accesses are contiguous across lanes.  D is replicated per phase in the
+// parameter block (8 KB at Nq = 16; see line8x2 in k1_ax8.cu for why) and read through uniform registers.
 #pragma once
 
 #include <cstring>
@@ -19,7 +30,7 @@ namespace semb {
 
 template <int NQ>
 struct DMatL {
-  double d[5][NQ * NQ];
+  double d[4][NQ * NQ];
 };
 
 template <int NQ>
@@ -28,10 +39,12 @@ struct AxlCfg {
   static constexpr int RS = V2 ? ((NQ % 4 == 2) ? NQ : NQ + 2) : NQ;
   static constexpr int PS = NQ * RS;
   static constexpr int ARR = NQ * PS;
-  static constexpr int SMEM = 2 * ARR * (int)sizeof(double);
+  static constexpr int SMEM = 3 * ARR * (int)sizeof(double);
   static constexpr int NT = NQ * NQ;
-  // registers, not shared memory, set the residency: 128 registers per thread need <= 512 threads per SM
-  static constexpr int MINB = (512 / NT) > 0 ? (512 / NT) : 1;
+  // registers and shared memory set the residency: <= 512 threads of 128 registers, <= 227 KB per SM
+  static constexpr int BY_REGS = (512 / NT) > 0 ? (512 / NT) : 1;
+  static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024) > 0 ? (227 * 1024) / (SMEM + 1024) : 1;
+  static constexpr int MINB = BY_REGS < BY_SMEM ? BY_REGS : BY_SMEM;
 };
 
 template <int NQ, bool TRANSPOSE>
@@ -45,6 +58,50 @@ __device__ __forceinline__ void line_contract(const double (&D)[NQ * NQ], const 
   }
 }
 
+// One pass over an r-line (contiguous, `row_in` -> `row_out`) and an s-line (stride RS, `col_in` -> `col_out`)
+// with the same D: out[o] = sum_m D[o][m] in[m] (or D[m][o] with TRANSPOSE).  Results are stored as soon as
+// they are complete (two outputs at a time where the row store can be 128 bits wide).
+template <int NQ, bool TRANSPOSE>
+__device__ __forceinline__ void line_pair(const double (&D)[NQ * NQ], const double* row_in, double* row_out,
+                                          const double* col_in, double* col_out) {
+  using C = AxlCfg<NQ>;
+  constexpr int RS = C::RS;
+  double ar[NQ], as[NQ];
+  if (C::V2) {
+#pragma unroll
+    for (int c = 0; c < NQ / 2; ++c) {
+      const double2 v = lds2(row_in + 2 * c);
+      ar[2 * c] = v.x;
+      ar[2 * c + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) ar[c] = row_in[c];
+  }
+#pragma unroll
+  for (int m = 0; m < NQ; ++m) as[m] = col_in[m * RS];
+  constexpr int STEP = C::V2 ? 2 : 1;
+#pragma unroll
+  for (int o = 0; o < NQ; o += STEP) {
+    double sr[STEP], ss[STEP];
+#pragma unroll
+    for (int q = 0; q < STEP; ++q) sr[q] = ss[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NQ; ++m) {
+#pragma unroll
+      for (int q = 0; q < STEP; ++q) {
+        const double d = TRANSPOSE ? D[m * NQ + o + q] : D[(o + q) * NQ + m];
+        sr[q] = fma(d, ar[m], sr[q]);
+        ss[q] = fma(d, as[m], ss[q]);
+      }
+    }
+    if (C::V2) sts2(row_out + o, make_double2(sr[0], sr[STEP - 1]));
+    else row_out[o] = sr[0];
+#pragma unroll
+    for (int q = 0; q < STEP; ++q) col_out[(o + q) * RS] = ss[q];
+  }
+}
+
 template <int NQ, bool MASK, bool DOT, int DIR>
 __global__ void __launch_bounds__(AxlCfg<NQ>::NT, AxlCfg<NQ>::MINB)
 axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> Dp) {
@@ -54,14 +111,14 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   extern __shared__ __align__(16) double smem[];
   double* A = smem;
   double* B = smem + C::ARR;
+  double* Cc = smem + 2 * C::ARR;
   const int tid = threadIdx.x;
   const int64_t e = a.e0 + blockIdx.x;
   const double* ue = a.u + e * NP;
   const double* ge = a.G6 + e * (int64_t)(6 * NP);
-  const int l2_prefetch = a.l2_prefetch;
 
   // bulk L2 prefetch of the element's block of G (see ax8_kernel)
-  if (l2_prefetch) {
+  if (a.l2_prefetch) {
     if ((NP % 2) == 0) {
       if (tid < 6) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge + tid * NP), "r"(NP * 8) : "memory");
     } else if (tid == 0) {
@@ -74,9 +131,8 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   const int t_g = tj * NQ + ti;   // inside a k-plane, global
   const int t_s = tj * RS + ti;   // inside a k-plane, shared
   // R layout: line (j = ti, k = tj) ; S layout: line (i = ti, k = tj)
-  double* rowA = A + tj * PS + ti * RS;
-  double* colA = A + tj * PS + ti;
-  double* colB = B + tj * PS + ti;
+  const int row = tj * PS + ti * RS;
+  const int col = tj * PS + ti;
 
   // P1: u -> registers (T) and shared; first plane of G
   double uc[NQ];
@@ -103,115 +159,64 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   for (int k = 0; k < NQ; ++k) A[k * PS + t_s] = uc[k];
   __syncthreads();
 
-  // P2a: s-derivative, A -> B
-  {
-    double a[NQ], o[NQ];
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) a[m] = colA[m * RS];
-    line_contract<NQ, false>(Dp.d[0], a, o);
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) colB[m * RS] = o[m];
-  }
-  __syncthreads();
-  // P2b: r-derivative, in place on A (each line is private to its thread)
-  {
-    double a[NQ], o[NQ];
-    if (C::V2) {
-#pragma unroll
-      for (int c = 0; c < NQ / 2; ++c) {
-        const double2 v = lds2(rowA + 2 * c);
-        a[2 * c] = v.x;
-        a[2 * c + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < NQ; ++c) a[c] = rowA[c];
-    }
-    line_contract<NQ, false>(Dp.d[1], a, o);
-    if (C::V2) {
-#pragma unroll
-      for (int c = 0; c < NQ / 2; ++c) sts2(rowA + 2 * c, make_double2(o[2 * c], o[2 * c + 1]));
-    } else {
-#pragma unroll
-      for (int c = 0; c < NQ; ++c) rowA[c] = o[c];
-    }
-  }
+  // P2: u_r (A rows -> C rows) and u_s (A columns -> B columns), one shared sweep over D
+  line_pair<NQ, false>(Dp.d[0], A + row, Cc + row, A + col, B + col);
   __syncthreads();
 
-  // P3: t-derivative in registers, G, start of D^T_t; wr -> A, ws -> B (own locations only)
-  double acc[NQ];
-#pragma unroll
-  for (int k = 0; k < NQ; ++k) acc[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < NQ; ++k) {
-    if (k < NQ - 1) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) gn[c] = __ldcs(ge + c * NP + (k + 1) * NT + t_g);
-    }
-    const double ur = A[k * PS + t_s];
-    const double us = B[k * PS + t_s];
-    double ut = 0.0;
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) ut = fma(Dp.d[2][k * NQ + m], uc[m], ut);
-    const double wr = g[0] * ur + g[1] * us + g[2] * ut;
-    const double ws = g[1] * ur + g[3] * us + g[4] * ut;
-    const double wt = g[2] * ur + g[4] * us + g[5] * ut;
-    A[k * PS + t_s] = wr;
-    B[k * PS + t_s] = ws;
-#pragma unroll
-    for (int kk = 0; kk < NQ; ++kk) acc[kk] = fma(Dp.d[2][k * NQ + kk], wt, acc[kk]);
-    if (k < NQ - 1) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) g[c] = gn[c];
-    }
-    __syncwarp();  // scheduling fence: keeps the compiler from hoisting every plane's G loads
-  }
-  __syncthreads();
-
-  // P4: D^T along r (A, in place) and along s (B, in place)
-  {
-    double a[NQ], o[NQ];
-    if (C::V2) {
-#pragma unroll
-      for (int c = 0; c < NQ / 2; ++c) {
-        const double2 v = lds2(rowA + 2 * c);
-        a[2 * c] = v.x;
-        a[2 * c + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < NQ; ++c) a[c] = rowA[c];
-    }
-    line_contract<NQ, true>(Dp.d[3], a, o);
-    if (C::V2) {
-#pragma unroll
-      for (int c = 0; c < NQ / 2; ++c) sts2(rowA + 2 * c, make_double2(o[2 * c], o[2 * c + 1]));
-    } else {
-#pragma unroll
-      for (int c = 0; c < NQ; ++c) rowA[c] = o[c];
-    }
-  }
-  {
-    double a[NQ], o[NQ];
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) a[m] = colB[m * RS];
-    line_contract<NQ, true>(Dp.d[4], a, o);
-#pragma unroll
-    for (int m = 0; m < NQ; ++m) colB[m * RS] = o[m];
-  }
-  __syncthreads();
-
-  // P5: sum the three parts, mask, local dot, store
+  // P3: u_t in registers, G, (w_r, w_s, w_t) -> (A, B, C) at the thread's own location; p.Ap
   double dot = 0.0;
+  {
+    double ut[NQ];
+    line_contract<NQ, false>(Dp.d[1], uc, ut);
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      if (k < NQ - 1) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) gn[c] = __ldcs(ge + c * NP + (k + 1) * NT + t_g);
+      }
+      const double ur = Cc[k * PS + t_s];
+      const double us = B[k * PS + t_s];
+      const double wr = g[0] * ur + g[1] * us + g[2] * ut[k];
+      const double ws = g[1] * ur + g[3] * us + g[4] * ut[k];
+      const double wt = g[2] * ur + g[4] * us + g[5] * ut[k];
+      if (DOT) dot = fma(ur, wr, fma(us, ws, fma(ut[k], wt, dot)));
+      A[k * PS + t_s] = wr;
+      B[k * PS + t_s] = ws;
+      Cc[k * PS + t_s] = wt;
+      if (k < NQ - 1) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) g[c] = gn[c];
+      }
+      __syncwarp();  // scheduling fence: keeps the compiler from hoisting every plane's G loads
+    }
+  }
+  __syncthreads();
+
+  // P4: D^T along r (A rows, in place) and along s (B columns, in place) sharing D; D^T along t (C) -> registers
+  line_pair<NQ, true>(Dp.d[2], A + row, A + row, B + col, B + col);
+  double acc[NQ];
+  {
+    double at[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) at[k] = Cc[k * PS + t_s];
+    line_contract<NQ, true>(Dp.d[3], at, acc);
+  }
+  __syncthreads();
+
+  // P5: sum the three parts, mask, store
   double* we = a.w + e * NP;
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
     double o = (A[k * PS + t_s] + B[k * PS + t_s]) + acc[k];
     if (MASK) {
       const int64_t gi = e * NP + k * NT + t_g;
-      if ((__ldg(a.maskbits + (gi >> 5)) >> (gi & 31)) & 1u) o = 0.0;
+      if ((__ldg(a.maskbits + (gi >> 5)) >> (gi & 31)) & 1u) {
+        // the reference's dot is p . mask(Ap) (sempy/elliptic.py:49-51): take the masked rows out of
+        // (grad u)^T G (grad u) = u . Au.  Rare path (boundary nodes only); u comes back from memory.
+        if (DOT) dot = fma(-o, (DIR != 0 ? a.p_out : a.u)[gi], dot);
+        o = 0.0;
+      }
     }
-    if (DOT) dot = fma(o, uc[k], dot);
     we[k * NT + t_g] = o;
   }
   if (DOT) {
@@ -238,7 +243,7 @@ static int launch_axl_t(const AxArgs& a, const DMatL<NQ>& dl, cudaStream_t st, i
 template <int NQ>
 static int launch_axl_nq(const AxArgs& a, const DMat& D, bool mask, bool dot, int dir, cudaStream_t st, int device) {
   DMatL<NQ> dl;
-  for (int q = 0; q < 5; ++q)
+  for (int q = 0; q < 4; ++q)
     for (int r = 0; r < NQ; ++r) std::memcpy(&dl.d[q][r * NQ], &D.d[r * NQ], sizeof(double) * NQ);
   SEMB_CHECK((dot && (dir == 1 || dir == 2)) || (!dot && dir == 0), "launch_axl: unsupported variant");
   if (!dot) return mask ? launch_axl_t<NQ, true, false, 0>(a, dl, st, device) : launch_axl_t<NQ, false, false, 0>(a, dl, st, device);

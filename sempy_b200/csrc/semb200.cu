@@ -73,7 +73,10 @@ struct ProfScope {
   semb_ctx* c;
   int kind;
   cudaEvent_t stop = nullptr;
-  ProfScope(semb_ctx* ctx, int k) : c(ctx), kind(k) {
+  cudaStream_t st;
+  ProfScope(semb_ctx* ctx, int k, cudaStream_t stream = nullptr) : c(ctx), kind(k), st(stream) {
+    if (c == nullptr) return;  // bracket switched off by the caller
+    if (st == nullptr) st = c->stream;
     if (!c->prof.on || !(c->prof.mask & (1 << k))) return;
     Profile& p = c->prof;
     if (p.used[kind] == p.start[kind].size()) {
@@ -83,13 +86,13 @@ struct ProfScope {
       p.start[kind].push_back(a);
       p.stop[kind].push_back(b);
     }
-    cudaEventRecord(p.start[kind][p.used[kind]], c->stream);
+    cudaEventRecord(p.start[kind][p.used[kind]], st);
     stop = p.stop[kind][p.used[kind]];
     p.used[kind]++;
     p.launches[kind]++;
   }
   ~ProfScope() {
-    if (stop) cudaEventRecord(stop, c->stream);
+    if (stop) cudaEventRecord(stop, st);
   }
 };
 
@@ -120,9 +123,11 @@ static void drop_jacobi(semb_ctx* c) {
 // whose fixed-order sum of p.Ap ends up in s->pAp (reduce.cuh); dir: 1 / 2 fold the CG direction update
 // p <- r + beta p / p <- dinv r + beta p into the load phase.
 static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int dir, int64_t e0, int64_t e1,
-                     const double* r, const double* dinv, int cta_off, int ncta_total, const int* done) {
+                     const double* r, const double* dinv, int cta_off, int ncta_total, const int* done,
+                     cudaStream_t st = nullptr, bool prof = true) {
   if (e1 <= e0) return 0;
-  ProfScope ps(c, SEMB_K_AX);
+  if (st == nullptr) st = c->stream;
+  ProfScope ps(prof ? c : nullptr, SEMB_K_AX, st);
   c->launch_count++;
   AxArgs a;
   a.u = p;
@@ -140,9 +145,9 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
   a.e0 = e0;
   a.e1 = e1;
   a.l2_prefetch = g_ax_l2_prefetch;
-  if (c->Nq == 8) return launch_ax8(a, c->D, mask, dot, dir, c->stream, c->device);
-  if (c->Nq >= 9) return launch_axl(c->Nq, a, c->D, mask, dot, dir, c->stream, c->device);
-  return launch_ax_generic(c->Nq, a, c->D, mask, dot, dir, c->stream);
+  if (c->Nq == 8) return launch_ax8(a, c->D, mask, dot, dir, st, c->device);
+  if (c->Nq >= 9) return launch_axl(c->Nq, a, c->D, mask, dot, dir, st, c->device);
+  return launch_ax_generic(c->Nq, a, c->D, mask, dot, dir, st);
 }
 
 // ---- K2 dispatch -----------------------------------------------------------
@@ -1379,14 +1384,24 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
       // p = z + beta p; Ap = mask(A p); pAp = p.Ap (local copies)         (elliptic.py:70,48-51)
       // Ap = dssum(Ap)                                                  (elliptic.py:54)
       if (c->have_halo && p2p) {
-        // Peer-memory path, one stream, no NCCL call: the elements that touch the slab interface first; their
-        // interface sums are written straight into the neighbours' memory (halo_gather) and fly while the
-        // interior elements are computed; the scatter kernel then picks the neighbours' sums up from local
-        // memory and, in a passenger CTA of the same launch, all-reduces pAp.
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, nif, zsrc, dinv, 0, cta1 + cta2, done));
-        c->seq_halo++;
-        SEMB_TRY(halo_gather(c, Ap, c->stream, done));
-        SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done));
+        // Peer-memory path, no NCCL call.  The elements that touch the slab interface run on a second,
+        // high-priority stream, followed there by the kernel that sums this rank's interface copies and
+        // writes them straight into the neighbours' memory; the interior elements run at the same time
+        // on the main stream (the two launches share one fixed-order p.Ap reduction).  The main stream
+        // then sums the longer local segments, picks the neighbours' sums up from local memory
+        // (halo_scatter) and, in a passenger CTA of that launch, all-reduces pAp.
+        {
+          // timed as ONE logical operator application: fork -> join of the two concurrent launches
+          ProfScope ps(c, SEMB_K_AX);
+          SEMB_CUDA(cudaEventRecord(c->ev_if_done, c->stream));  // p, beta of the previous iteration are final
+          SEMB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_if_done, 0));
+          SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, 0, nif, zsrc, dinv, 0, cta1 + cta2, done, c->comm_stream, false));
+          c->seq_halo++;
+          SEMB_TRY(halo_gather(c, Ap, c->comm_stream, done));
+          SEMB_CUDA(cudaEventRecord(c->ev_gathered, c->comm_stream));
+          SEMB_TRY(launch_ax(c, p, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done, nullptr, false));
+          SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
+        }
         SEMB_TRY(launch_gs(c, Ap, done, pull));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done, &s->pAp, 1));
       } else if (c->have_halo) {
@@ -1563,7 +1578,9 @@ int semb_comm_init(semb_ctx* c, int nranks, int rank, const char* id128) {
   SEMB_NCCL(CommInitRank(&c->comm, nranks, id, rank));
   c->nranks = nranks;
   c->rank = rank;
-  SEMB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  SEMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  SEMB_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));  // interface work first
   SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_if_done, cudaEventDisableTiming));
   SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
   SEMB_CUDA(cudaEventCreateWithFlags(&c->ev_exchanged, cudaEventDisableTiming));

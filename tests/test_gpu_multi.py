@@ -23,12 +23,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, size, port, dims, perturb, N, out):
+def _worker(rank, size, port, dims, perturb, N, out, p2p="1"):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["SEMB_DEVICE"] = str(rank)
+    os.environ["SEMB_P2P"] = p2p  # read when libsemb200 is loaded (the worker is a fresh process)
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
         from oracle import sem_oracle as so
@@ -81,6 +82,10 @@ def _worker(rank, size, port, dims, perturb, N, out):
         if itg != ito:
             xg, _ = elliptic_pcg(m, take(b), tol=0.0, maxit=ito)
         errs["pcg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
+        # bitwise repeatable across two solves (fixed summation order on every rank and across ranks)
+        x1, it1 = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
+        x2, it2 = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
+        errs["repeatable"] = float(it1 == it2 and np.array_equal(x1, x2))
         res = comm.allgather(errs)
         if rank == 0:
             import json
@@ -91,13 +96,13 @@ def _worker(rank, size, port, dims, perturb, N, out):
         dist.destroy_process_group()
 
 
-def _run(size, dims, perturb, N, tmp_path):
+def _run(size, dims, perturb, N, tmp_path, p2p="1"):
     import json
 
     import torch.multiprocessing as mp
 
     out = str(tmp_path / "res.json")
-    mp.spawn(_worker, args=(size, _free_port(), dims, perturb, N, out), nprocs=size, join=True)
+    mp.spawn(_worker, args=(size, _free_port(), dims, perturb, N, out, p2p), nprocs=size, join=True)
     return json.load(open(out))
 
 
@@ -110,14 +115,17 @@ def test_four_rank_solver_matches_oracle(tmp_path):
         assert e["dssum"] < 1e-15 and e["ax_full"] <= 1e-12
         assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
         assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
+        assert e["repeatable"] == 1.0
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])  # peer-memory transport (default) and the NCCL fallback
 @pytest.mark.parametrize("dims,perturb,N", [((3, 3, 4), 0.3, 7), ((4, 3, 5), 0.2, 4)])
-def test_two_rank_solver_matches_oracle(dims, perturb, N, tmp_path):
+def test_two_rank_solver_matches_oracle(dims, perturb, N, p2p, tmp_path):
     if _ndev() < 2:
         pytest.skip("needs 2 GPUs")
-    for e in _run(2, dims, perturb, N, tmp_path):
+    for e in _run(2, dims, perturb, N, tmp_path, p2p):
         assert e["rmult"] == 0.0 and e["mask"] == 0.0
         assert e["dssum"] < 1e-15 and e["ax_full"] <= 1e-12
         assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
         assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
+        assert e["repeatable"] == 1.0
