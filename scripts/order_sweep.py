@@ -12,6 +12,9 @@ from sempy_b200 import _capi  # noqa: E402
 from sempy_b200.elliptic import _ax, elliptic_pcg  # noqa: E402
 from sempy_b200.mesh import box_mesh  # noqa: E402
 
+for kv in os.environ.get("KNOBS", "").split(","):
+    if kv:
+        _capi.check(_capi.lib().semb_set_tuning(kv.split("=")[0].encode(), int(kv.split("=")[1])))
 cases = [(int(a.split(":")[0]), int(a.split(":")[1])) for a in sys.argv[1:]] or [(7, 32), (15, 16), (10, 23), (3, 64)]
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for N, nel in cases:
