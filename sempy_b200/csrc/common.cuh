@@ -157,9 +157,11 @@ struct semb_ctx {
   int64_t gs_var_nseg = 0;
   int64_t gs_var_off = 0;
   bool have_gs = false;
-  // pull form of the two-copy segments: link[q] = 0x80000000 | the other copy's local index, 0 for every
-  // other node (and, once a halo is set, for nodes completed by the halo kernels)
+  // pull form: link[q] = GS_LINK_PAIR | the other copy's local index, GS_LINK_LONG | slot of the node's
+  // segment in gs_sums, or 0 (no other copy; once a halo is set also the nodes completed by the halo kernels)
   uint32_t* gs_link = nullptr;
+  double* gs_sums = nullptr;  // compact sums of the segments with more than two copies
+  bool pull_ok = false;       // fewer than 2^30 such segments
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 

@@ -152,8 +152,11 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 
 // ---- K2 dispatch -----------------------------------------------------------
 // in-place (push) form
-// skip_pairs: the two-copy segments are left to the consumer (pull form, gs_pair)
-static int launch_gs(semb_ctx* c, double* x, const int* done, bool skip_pairs = false) {
+// pull: the two-copy segments are left to the consumer and the longer ones only have their sums formed
+// (compact form, c->gs_sums), nothing is written back to x (pull form, gs_linked)
+static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false) {
+  const bool skip_pairs = pull;
+  double* sums = pull ? c->gs_sums : nullptr;
   ProfScope ps(c, SEMB_K_GS);
   GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
@@ -173,18 +176,19 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, bool skip_pairs = 
   const int total_blocks = plan.b2 + plan.b4 + plan.b8;
   if (total_blocks > 0) {
     c->launch_count++;
-    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done);
+    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done, sums);
     SEMB_CUDA(cudaGetLastError());
   }
   if (c->gs_var_nseg > 0) {
     c->launch_count++;
     gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
-                                                                      c->gs_var_nseg, done);
+                                                                      c->gs_var_nseg, done,
+                                                                      sums != nullptr ? sums + plan.n4 + plan.n8 : nullptr);
     SEMB_CUDA(cudaGetLastError());
   }
   return 0;
 }
-static inline bool use_pull(const semb_ctx* c) { return g_gs_pull != 0; }
+static inline bool use_pull(const semb_ctx* c) { return c->pull_ok && g_gs_pull != 0; }
 
 // ---- multi-GPU halo --------------------------------------------------------
 static inline bool use_p2p(const semb_ctx* c) { return c->p2p && g_p2p_on; }
@@ -590,6 +594,7 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->G6);
   cudaFree(c->gs_ids);
   cudaFree(c->gs_link);
+  cudaFree(c->gs_sums);
   cudaFree(c->gs_var_start);
   cudaFree(c->rmult);
   cudaFree(c->mult);
@@ -813,11 +818,15 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   const int64_t nids = align4(lay.off[3] + nvar_ids);
   SEMB_CHECK(nids < (int64_t)2147483647, "semb_set_gather_scatter: id table too long");
 
-  // 3. ids (copies of a segment in ascending local index) and the pair links of the pull form
+  // 3. ids (copies of a segment in ascending local index) and the links of the pull form
   cudaFree(c->gs_ids);
   cudaFree(c->gs_link);
+  cudaFree(c->gs_sums);
   c->gs_ids = nullptr;
   c->gs_link = nullptr;
+  c->gs_sums = nullptr;
+  c->pull_ok = n4 + n8 + nv < ((int64_t)1 << 30);
+  SEMB_CUDA(cudaMalloc(&c->gs_sums, sizeof(double) * (size_t)std::max<int64_t>(n4 + n8 + nv, 2)));
   SEMB_CUDA(cudaMalloc(&c->gs_ids, sizeof(int32_t) * (size_t)std::max<int64_t>(nids, 4)));
   SEMB_CUDA(cudaMemset(c->gs_ids, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(nids, 4)));
   SEMB_CUDA(cudaMalloc(&c->gs_link, sizeof(uint32_t) * (size_t)(n + 2)));
@@ -1437,7 +1446,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         ll.nranks = 1;
         if (tail && p2p) ll = ll_args(c, ++c->seq_scalar);
 #define SEMB_UPDATE(J, P)                                                                                               \
-  cg_update_kernel<J, P><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, c->gs_link, s, n, \
+  cg_update_kernel<J, P><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, Ap, c->mult, dinv, c->gs_link, c->gs_sums, s, n, \
                                                         c->partials, ticket, hist, ll)
         if (jac && pull) SEMB_UPDATE(true, true);
         else if (jac) SEMB_UPDATE(true, false);

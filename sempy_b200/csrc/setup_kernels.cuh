@@ -179,7 +179,7 @@ struct SegLayout {
   int64_t off[4];   // start of each class in ids (multiples of 4 ints)
 };
 
-// writes the ids of every shared segment (ascending) and the pair links of the two-copy segments
+// writes the ids of every shared segment (ascending) and the links of the pull form (vec_kernels.cuh)
 __global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t* __restrict__ g2l,
                                 const int64_t* __restrict__ gstart, const SegLayout lay, const int32_t* __restrict__ var_start,
                                 int32_t* __restrict__ ids, uint32_t* __restrict__ link) {
@@ -204,6 +204,9 @@ __global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t*
     if (len == 2) {  // pair links of the pull form: each copy points at the other (GS_LINK_PAIR)
       link[out[0]] = 0x80000000u | (uint32_t)out[1];
       link[out[1]] = 0x80000000u | (uint32_t)out[0];
+    } else {  // longer segments: every copy points at its segment's slot in the compact sums (GS_LINK_LONG)
+      const uint32_t lk = 0x40000000u | (uint32_t)(t - lay.b[1]);
+      for (int c = 0; c < len; ++c) link[out[c]] = lk;
     }
   }
 }

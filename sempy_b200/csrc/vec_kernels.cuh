@@ -40,9 +40,11 @@ __device__ __forceinline__ void gs_load_ids(const int32_t* __restrict__ ids, int
 // U segments per thread, all index loads first, then all gathers, then sums and stores: the pass is
 // latency-bound (ncu: 48 % DRAM at exactly the sector-level traffic), so memory-level parallelism per
 // thread is what counts.
+// sums != nullptr (compact form): the sum of segment s goes to sums[s] only and x is left untouched -- the
+// consumer picks it up through its node links -- which halves the scattered sector traffic of the pass.
 template <int L, int U>
 __device__ __forceinline__ void gs_segments(double* __restrict__ x, const int32_t* __restrict__ ids, int64_t first,
-                                            int64_t stride, int64_t nseg) {
+                                            int64_t stride, int64_t nseg, double* __restrict__ sums = nullptr) {
   int id[U][L];
   double v[U][L];
 #pragma unroll
@@ -63,8 +65,12 @@ __device__ __forceinline__ void gs_segments(double* __restrict__ x, const int32_
       double sum = v[u][0];
 #pragma unroll
       for (int c = 1; c < L; ++c) sum += v[u][c];
+      if (sums != nullptr) {
+        sums[first + u * stride] = sum;
+      } else {
 #pragma unroll
-      for (int c = 0; c < L; ++c) x[id[u][c]] = sum;
+        for (int c = 0; c < L; ++c) x[id[u][c]] = sum;
+      }
     }
   }
 }
@@ -78,9 +84,11 @@ struct GsPlan {
   int b2, b4, b8;            // blocks per class
 };
 
+// sums (compact form, len-4 and len-8 classes only): segment s of class 4 -> sums[s], of class 8 ->
+// sums[n4 + s]; the irregular rest follows at sums[n4 + n8 + s] (gs_var_kernel).
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
-                const int* __restrict__ done) {
+                const int* __restrict__ done, double* __restrict__ sums) {
   if (done != nullptr && *done) return;
   int b = blockIdx.x;
   if (b < plan.b2) {
@@ -93,44 +101,59 @@ gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const G
   if (b < plan.b4) {
     const int64_t stride = (int64_t)plan.b4 * VEC_NT;
     for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n4; t += 2 * stride)
-      gs_segments<4, 2>(x, ids + plan.off4, t, stride, plan.n4);
+      gs_segments<4, 2>(x, ids + plan.off4, t, stride, plan.n4, sums);
     return;
   }
   b -= plan.b4;
   const int64_t stride = (int64_t)plan.b8 * VEC_NT;
   for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n8; t += stride)
-    gs_segments<8, 1>(x, ids + plan.off8, t, stride, plan.n8);
+    gs_segments<8, 1>(x, ids + plan.off8, t, stride, plan.n8, sums != nullptr ? sums + plan.n4 : nullptr);
 }
 
 // Segments of any other length (unstructured meshes): CSR offsets.
 __global__ void __launch_bounds__(VEC_NT)
 gs_var_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const int32_t* __restrict__ start,
-              int64_t nseg, const int* __restrict__ done) {
+              int64_t nseg, const int* __restrict__ done, double* __restrict__ sums) {
   if (done != nullptr && *done) return;
   for (int64_t s = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * VEC_NT) {
     const int lo = start[s], hi = start[s + 1];
     double sum = 0.0;
     for (int q = lo; q < hi; ++q) sum += x[ids[q]];
-    for (int q = lo; q < hi; ++q) x[ids[q]] = sum;
+    if (sums != nullptr) {
+      sums[s] = sum;
+    } else {
+      for (int q = lo; q < hi; ++q) x[ids[q]] = sum;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
-// Pull form for the segments with exactly two copies (73 % of the shared nodes of a hex mesh at N = 7:
-// the face-interior nodes).  link[q] = 0x80000000 | local index of node q's only other copy, 0 otherwise
-// (no other copy, a longer segment, or a node that the halo kernels complete).  The consumer of a
-// gather-scattered vector adds the partner's value to its own while it streams through: one predicated
-// gather per node, no index table, no divergence; a + b is commutative in IEEE arithmetic, so both copies
-// get the bitwise identical sum, nothing is written back and the pass over the len-2 class of K2
-// disappears.  Longer segments (edges, vertices: 16 % of the nodes) keep the in-place push form, run
-// BEFORE the consumer on their own class only (gs_fixed_kernel with n2 = 0).  Inside semb_cg the consumer
-// is the update kernel (r -= alpha * dssum(Ap)).  The gathers hit L2: the partner sits in a
+// Pull form.  The consumer of a gather-scattered vector completes the sums while it streams through the
+// vector, guided by one 32-bit link per node:
+//   0                       : no other copy (or a node that the halo kernels complete): the value as it is
+//   GS_LINK_PAIR | index    : exactly one other copy (73 % of the shared nodes of a hex mesh at N = 7, the
+//                             face-interior nodes): own value + the partner's UNSUMMED value.  a + b commutes
+//                             in IEEE arithmetic, so both copies get the bitwise identical sum.
+//   GS_LINK_LONG | segment  : more copies (edges, vertices: 16 % of the nodes): the sum of the node's segment,
+//                             formed BEFORE the consumer by the compact form of gs_fixed_kernel / gs_var_kernel
+//                             (copies added in ascending local index, one 8-byte store per segment into a
+//                             small L2-resident array instead of a scattered write-back to every copy).
+// One predicated gather per node, no index table, no divergence, nothing written back to the vector: the
+// in-place pass over the len-2 class disappears and the rest moves half its sectors.  Inside semb_cg the
+// consumer is the update kernel (r -= alpha * dssum(Ap)).  The pair gathers hit L2: the partner sits in a
 // neighbouring element that the same pass streams through.
 // ---------------------------------------------------------------------------
 constexpr uint32_t GS_LINK_PAIR = 0x80000000u;
+constexpr uint32_t GS_LINK_LONG = 0x40000000u;
+constexpr uint32_t GS_LINK_INDEX = 0x3fffffffu;
 
-__device__ __forceinline__ double gs_pair(const double* __restrict__ v, uint32_t link) {
-  return (link & GS_LINK_PAIR) ? v[link & ~GS_LINK_PAIR] : 0.0;
+// value of dssum(v) at a node with link `link` and own (unsummed) value `own`
+__device__ __forceinline__ double gs_linked(const double* __restrict__ v, const double* __restrict__ sums, uint32_t link,
+                                            double own) {
+  if (link == 0u) return own;
+  const bool pair = (link & GS_LINK_PAIR) != 0u;
+  const double other = pair ? v[link & ~GS_LINK_PAIR] : sums[link & GS_LINK_INDEX];
+  return pair ? own + other : other;
 }
 
 // link[copy] = 0 for the copies of interface nodes (their sum is completed by the halo kernels)
@@ -475,9 +498,10 @@ __device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* par
 // ---------------------------------------------------------------------------
 // K3: x += alpha p ; r -= alpha dssum(Ap) ; partial of sum rmult r r (or rmult r dinv r)
 // (sempy/elliptic.py:52-60; iterative.py:66-73).  With PULL the pairwise part of the gather-scatter of Ap
-// (elliptic.py:54) happens here: nodes with exactly one other copy add the partner's UNSUMMED operator
-// output on the fly (gs_pair), so that part of Ap is neither re-read by a separate pass nor written back.
-// 57 B per node with Jacobi (+4 link with PULL, + the partner sectors from L2).
+// (elliptic.py:54) is completed here: nodes with exactly one other copy add the partner's UNSUMMED operator
+// output on the fly, nodes of longer segments take their segment's sum from the compact array (gs_linked),
+// so Ap is neither re-read by a separate full pass nor written back.
+// 57 B per node with Jacobi (+4 link with PULL, + the partner / segment-sum sectors from L2).
 // ---------------------------------------------------------------------------
 // The weight rmult = 1/multiplicity is read as a one-byte copy count (1 B instead of 8 B per node) and
 // turned back into the identical double through a small shared-memory table of 1.0/c (a division in
@@ -487,7 +511,7 @@ template <bool JACOBI, bool PULL>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                  const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
-                 const uint32_t* __restrict__ link, CgScalars* __restrict__ s, int64_t n,
+                 const uint32_t* __restrict__ link, const double* __restrict__ sums, CgScalars* __restrict__ s, int64_t n,
                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ hist,
                  const LlArgs ll) {
   if (s->done) return;
@@ -506,19 +530,14 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   const uint2* l2 = reinterpret_cast<const uint2*>(link);
   for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
     double2 av = a2[q];
-    double2 pa = make_double2(0.0, 0.0);
     if (PULL) {
       const uint2 lk = __ldg(l2 + q);
-      pa.x = gs_pair(Ap, lk.x);
-      pa.y = gs_pair(Ap, lk.y);
+      av.x = gs_linked(Ap, sums, lk.x, av.x);
+      av.y = gs_linked(Ap, sums, lk.y, av.y);
     }
     const double2 pv = p2[q];
     const uchar2 mc = m2[q];
     double2 xv = x2[q], rv = r2[q];
-    if (PULL) {
-      av.x += pa.x;
-      av.y += pa.y;
-    }
     xv.x = xv.x + alpha * pv.x;
     xv.y = xv.y + alpha * pv.y;
     rv.x = rv.x - alpha * av.x;
@@ -538,7 +557,7 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t q = n - 1;
     double av = Ap[q];
-    if (PULL) av += gs_pair(Ap, link[q]);
+    if (PULL) av = gs_linked(Ap, sums, link[q], av);
     const double xv = x[q] + alpha * p[q];
     const double rv = r[q] - alpha * av;
     x[q] = xv;
