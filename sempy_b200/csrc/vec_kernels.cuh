@@ -147,13 +147,24 @@ constexpr uint32_t GS_LINK_PAIR = 0x80000000u;
 constexpr uint32_t GS_LINK_LONG = 0x40000000u;
 constexpr uint32_t GS_LINK_INDEX = 0x3fffffffu;
 
-// value of dssum(v) at a node with link `link` and own (unsummed) value `own`
+// The other operand of a linked node -- the partner's value or the segment's sum -- or 0.0 without a link.
+// A predicated load (no branch): the gathers of a thread's nodes are issued back to back with its
+// streaming loads instead of being serialised in divergent branches ahead of them.
+__device__ __forceinline__ double gs_other(const double* __restrict__ v, const double* __restrict__ sums, uint32_t link) {
+  const double* src = (link & GS_LINK_PAIR) ? v + (link & ~GS_LINK_PAIR) : sums + (link & GS_LINK_INDEX);
+  double o;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.f64 %0, [%1];\n\t}"
+      : "=d"(o)
+      : "l"(src), "r"(link));
+  return o;
+}
+// value of dssum(v) at a node with link `link`, own (unsummed) value `own` and other operand `other`
+__device__ __forceinline__ double gs_combine(uint32_t link, double own, double other) {
+  return (link & GS_LINK_PAIR) ? own + other : (link & GS_LINK_LONG) ? other : own;
+}
 __device__ __forceinline__ double gs_linked(const double* __restrict__ v, const double* __restrict__ sums, uint32_t link,
                                             double own) {
-  if (link == 0u) return own;
-  const bool pair = (link & GS_LINK_PAIR) != 0u;
-  const double other = pair ? v[link & ~GS_LINK_PAIR] : sums[link & GS_LINK_INDEX];
-  return pair ? own + other : other;
+  return gs_combine(link, own, gs_other(v, sums, link));
 }
 
 // link[copy] = 0 for the copies of interface nodes (their sum is completed by the halo kernels)
@@ -529,15 +540,21 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
   const uint2* l2 = reinterpret_cast<const uint2*>(link);
   for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n2; q += (int64_t)gridDim.x * VEC_NT) {
-    double2 av = a2[q];
+    uint2 lk = make_uint2(0u, 0u);
+    double2 ov = make_double2(0.0, 0.0);
     if (PULL) {
-      const uint2 lk = __ldg(l2 + q);
-      av.x = gs_linked(Ap, sums, lk.x, av.x);
-      av.y = gs_linked(Ap, sums, lk.y, av.y);
+      lk = __ldg(l2 + q);
+      ov.x = gs_other(Ap, sums, lk.x);
+      ov.y = gs_other(Ap, sums, lk.y);
     }
+    double2 av = a2[q];
     const double2 pv = p2[q];
     const uchar2 mc = m2[q];
     double2 xv = x2[q], rv = r2[q];
+    if (PULL) {
+      av.x = gs_combine(lk.x, av.x, ov.x);
+      av.y = gs_combine(lk.y, av.y, ov.y);
+    }
     xv.x = xv.x + alpha * pv.x;
     xv.y = xv.y + alpha * pv.y;
     rv.x = rv.x - alpha * av.x;

@@ -139,13 +139,21 @@ def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     counts = np.array([p.shape[0] for p in parts], dtype=np.int64)
     offs = np.concatenate(([0], np.cumsum(counts)))
     allc = np.concatenate(parts, axis=0)
-    if allc.shape[0] == 0:
+    if allc.shape[0] == 0 or mine.shape[0] == 0:
         return empty
-    # the reference's rule on the union: identical on every rank
-    gid_all, _, gs_all = numbering(allc[:, 0][None, :], allc[:, 1][None, :], allc[:, 2][None, :])
-    grp = gid_all.reshape(-1).astype(np.int64) - 1
     owner = np.repeat(np.arange(size), counts)
     pos = np.arange(allc.shape[0]) - offs[owner]
+    # Only points inside the bounding box of MY candidates can share a node with me (the matching
+    # tolerance is 1e-6 in distance): drop the rest before sorting.  Every member of each of my groups
+    # survives on every rank that owns one of them, and the order of two groups is decided by their own
+    # members' coordinates, so both sides of an interface still list their shared nodes in the same order.
+    lo, hi = mine.min(axis=0) - 1e-5, mine.max(axis=0) + 1e-5
+    near = np.all((allc >= lo) & (allc <= hi), axis=1)
+    allc, owner, pos = allc[near], owner[near], pos[near]
+    # the reference's rule on the union
+    gid_all, _, gs_all = numbering(np.ascontiguousarray(allc[:, 0])[None, :], np.ascontiguousarray(allc[:, 1])[None, :],
+                                   np.ascontiguousarray(allc[:, 2])[None, :])
+    grp = gid_all.reshape(-1).astype(np.int64) - 1
     multi = np.diff(gs_all)[grp] >= 2
     grp, owner, pos = grp[multi], owner[multi], pos[multi]
     # a group must not hold two entries of one rank (the local numbering already merged those)

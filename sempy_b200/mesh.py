@@ -515,8 +515,9 @@ class Mesh:
                 lead.append(a._host.reshape(self.num_elements, Np)[:ne])
             else:
                 lead.append(a._dev.to_host(ne * Np).reshape(ne, Np))
-        self._halo = distributed.build_halo(self.comm, lead[0], lead[1], lead[2], cand, lead[3],
-                                            global_numbering_from_coordinates)
+        # the union of all ranks' candidates is numbered with the same rule -- on the device when set-up runs there
+        number = global_numbering_device if device_setup_enabled() else global_numbering_from_coordinates
+        self._halo = distributed.build_halo(self.comm, lead[0], lead[1], lead[2], cand, lead[3], number)
 
     def setup_mask(self):
         """Homogeneous Dirichlet mask of the bounding box (sempy/mesh.py:449-477); with several ranks the box
