@@ -162,6 +162,12 @@ struct semb_ctx {
   uint32_t* gs_link = nullptr;
   double* gs_sums = nullptr;  // compact sums of the segments with more than two copies
   bool pull_ok = false;       // fewer than 2^30 such segments
+  // compact edge buffer (ax_common.cuh: eb_slot): the operator kernel's second copy of the edge / vertex values
+  // and the ids of the longer segments as positions in it (indexed like gs_ids, shifted by the len-4 class offset)
+  double* eb = nullptr;
+  int32_t* eb_ids = nullptr;
+  int64_t eb_ids_off = 0;
+  bool eb_ok = false;
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 

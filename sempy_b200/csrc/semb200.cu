@@ -33,6 +33,9 @@ static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
 // "gs_pull": 0 = the whole gather-scatter as a separate in-place pass (push form) instead of summing the
 // two-copy segments inside the consumer (CG update kernel)
 static int g_gs_pull = env_int("SEMB_GS_PULL", 1);
+// "edge_buffer": 0 = the compact gather-scatter reads the operator output itself instead of the dense
+// edge buffer written by the operator kernel (N = 7 only)
+static int g_edge_buffer = env_int("SEMB_EDGE_BUFFER", 1);
 
 const NcclApi& nccl() {
   static NcclApi api = [] {
@@ -118,6 +121,10 @@ static void drop_jacobi(semb_ctx* c) {
   c->fdm_ready = false;
 }
 
+static inline bool use_pull(const semb_ctx* c) { return c->pull_ok && g_gs_pull != 0; }
+// the edge buffer is written by ax8_kernel only and read by the compact (pull) form of the gather-scatter
+static inline bool use_eb(const semb_ctx* c) { return c->eb_ok && c->Nq == 8 && g_edge_buffer != 0 && use_pull(c); }
+
 // ---- K1 dispatch -----------------------------------------------------------
 // One launch over the elements [e0, e1).  dot: the launch is part of a logical grid of ncta_total CTAs
 // whose fixed-order sum of p.Ap ends up in s->pAp (reduce.cuh); dir: 1 / 2 fold the CG direction update
@@ -137,6 +144,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
   a.G6 = c->G6;
   a.w = ap;
   a.maskbits = c->maskbits;
+  a.eb = (dot && use_eb(c)) ? c->eb : nullptr;
   a.s = c->scal;
   a.done = done;
   a.red = GridRed{c->partials, c->partials2, c->ticket};
@@ -157,6 +165,11 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false) {
   const bool skip_pairs = pull;
   double* sums = pull ? c->gs_sums : nullptr;
+  const int32_t* ids = c->gs_ids;
+  if (pull && use_eb(c)) {  // read the dense edge buffer (written by the operator launch just before)
+    x = c->eb;
+    ids = c->eb_ids - c->eb_ids_off;
+  }
   ProfScope ps(c, SEMB_K_GS);
   GsPlan plan{0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (const GsClass& k : c->gs_classes) {
@@ -176,19 +189,18 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false)
   const int total_blocks = plan.b2 + plan.b4 + plan.b8;
   if (total_blocks > 0) {
     c->launch_count++;
-    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done, sums);
+    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, ids, plan, done, sums);
     SEMB_CUDA(cudaGetLastError());
   }
   if (c->gs_var_nseg > 0) {
     c->launch_count++;
-    gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, c->gs_ids + c->gs_var_off, c->gs_var_start,
+    gs_var_kernel<<<vec_grid(c->gs_var_nseg), VEC_NT, 0, c->stream>>>(x, ids + c->gs_var_off, c->gs_var_start,
                                                                       c->gs_var_nseg, done,
                                                                       sums != nullptr ? sums + plan.n4 + plan.n8 : nullptr);
     SEMB_CUDA(cudaGetLastError());
   }
   return 0;
 }
-static inline bool use_pull(const semb_ctx* c) { return c->pull_ok && g_gs_pull != 0; }
 
 // ---- multi-GPU halo --------------------------------------------------------
 static inline bool use_p2p(const semb_ctx* c) { return c->p2p && g_p2p_on; }
@@ -595,6 +607,8 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->gs_ids);
   cudaFree(c->gs_link);
   cudaFree(c->gs_sums);
+  cudaFree(c->eb);
+  cudaFree(c->eb_ids);
   cudaFree(c->gs_var_start);
   cudaFree(c->rmult);
   cudaFree(c->mult);
@@ -834,6 +848,29 @@ int semb_set_gather_scatter(semb_ctx* c, const int64_t* g2l, const int64_t* gsta
   if (lay.b[4] > 0) {
     seg_emit_kernel<<<vec_grid(lay.b[4]), VEC_NT>>>(sorted, d_g2l, d_gst, lay, c->gs_var_start, c->gs_ids, c->gs_link);
     SEMB_CUDA(cudaGetLastError());
+  }
+  // 4. the longer segments as positions in the compact edge buffer (hex elements only: Nq >= 2)
+  cudaFree(c->eb);
+  cudaFree(c->eb_ids);
+  c->eb = nullptr;
+  c->eb_ids = nullptr;
+  c->eb_ok = false;
+  c->eb_ids_off = lay.off[1];
+  if (c->Nq >= 2 && nids > lay.off[1] && c->E * (int64_t)eb_count(c->Nq) < (int64_t)2147483647) {
+    const int64_t cnt = nids - lay.off[1];
+    SEMB_CUDA(cudaMalloc(&c->eb_ids, sizeof(int32_t) * (size_t)cnt));
+    SEMB_CUDA(cudaMemset(info.p, 0, 4 * sizeof(int)));
+    eb_ids_kernel<<<vec_grid(cnt), VEC_NT>>>(c->gs_ids + lay.off[1], cnt, c->Nq, c->eb_ids, info.as<int>());
+    SEMB_CUDA(cudaGetLastError());
+    SEMB_CUDA(cudaMemcpy(h_info, info.p, sizeof(h_info), cudaMemcpyDeviceToHost));
+    c->eb_ok = (h_info[0] & 4) == 0;
+    if (c->eb_ok) {
+      SEMB_CUDA(cudaMalloc(&c->eb, sizeof(double) * (size_t)(c->E * eb_count(c->Nq))));
+      SEMB_CUDA(cudaMemset(c->eb, 0, sizeof(double) * (size_t)(c->E * eb_count(c->Nq))));
+    } else {
+      cudaFree(c->eb_ids);
+      c->eb_ids = nullptr;
+    }
   }
   SEMB_CUDA(cudaDeviceSynchronize());  // tables complete before the context's (non-blocking) stream uses them
   c->gs_classes.clear();
@@ -1787,6 +1824,10 @@ int semb_set_tuning(const char* name, int value) {
   }
   if (std::strcmp(name, "gs_pull") == 0) {
     g_gs_pull = value;
+    return 0;
+  }
+  if (std::strcmp(name, "edge_buffer") == 0) {
+    g_edge_buffer = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {

@@ -490,3 +490,54 @@ def test_fdm_preconditioner_vs_oracle(dims, perturb, N):
     assert rel_inf(xg, xj) < 1e-7
     if N >= 3:
         assert itg < itj, (itg, itj)
+
+
+@pytest.mark.parametrize("N", [7, 4, 10])
+def test_irregular_multiplicities_vs_oracle(N):
+    """A box with elements removed (L-shaped in every direction): nodes with 3, 5, 6 and 7 copies exercise the
+    CSR gather-scatter class in its in-place form (dssum) and its compact form (inside the CG loop)."""
+    from sempy_b200 import _capi
+    from sempy_b200.elliptic import elliptic_ax, elliptic_cg, elliptic_pcg
+    from sempy_b200.mesh import Mesh, box_mesh_arrays
+
+    pts, hexes = box_mesh_arrays(3, 3, 2, perturb=0.2, seed=9)
+    keep = np.ones(len(hexes), bool)
+    keep[[0, 4, 13, 17]] = False  # corners of the two layers and the centre of the upper one
+    m = Mesh.from_arrays(pts, hexes[keep])
+    m.find_physical_coordinates(N)
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    m.setup_mask()
+    g2l, gs = m.get_global_to_local_map()
+    counts = np.unique(np.diff(gs))
+    assert {3, 5, 6, 7} & set(counts.tolist()), counts  # irregular segment lengths are present
+    D = np.ascontiguousarray(__import__("sempy_b200.derivative", fromlist=["x"]).reference_derivative_matrix(N))
+    geom = m.get_geom()
+    rng = np.random.default_rng(12)
+    p = rng.standard_normal(m.get_num_elems() * m.Np)
+    x = p.copy()
+    m.dssum(x)
+    assert rel_inf(x, so.gather_scatter(p, g2l, gs)) < 1e-15
+    assert np.array_equal(m.get_rmult(), so.multiplicity_inverse(g2l, gs))
+    b = m.apply_mask(m.dssum(rng.standard_normal(p.size)))
+    axo = lambda v: so.elliptic_ax_batched(geom, v, N, D)
+    xo, ito = so.elliptic_cg(axo, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-10, maxit=3000)
+    lib = _capi.lib()
+    sols = []
+    for pull in (1, 0):
+        _capi.check(lib.semb_set_tuning(b"gs_pull", pull))
+        xg, itg = elliptic_cg(m, b, tol=1e-10, maxit=3000)
+        assert abs(itg - ito) <= 1
+        if itg != ito:
+            xg, itg = elliptic_cg(m, b, tol=0.0, maxit=ito)
+        assert rel_inf(xg, xo) < 1e-10
+        sols.append(xg)
+    _capi.check(lib.semb_set_tuning(b"gs_pull", 1))
+    assert np.array_equal(sols[0], sols[1])
+    dinv = m.mask / so.gather_scatter(so.jacobi_diagonal(geom, N, D), g2l, gs)
+    xo, ito = so.elliptic_pcg_jacobi(axo, dinv, m.mask, g2l, gs, m.get_rmult(), b, tol=1e-10, maxit=3000)
+    xg, itg = elliptic_pcg(m, b, tol=1e-10, maxit=3000)
+    assert abs(itg - ito) <= 1
+    if itg != ito:
+        xg, itg = elliptic_pcg(m, b, tol=0.0, maxit=ito)
+    assert rel_inf(xg, xo) < 1e-10
