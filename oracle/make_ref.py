@@ -33,6 +33,8 @@ def make(ref=REF, dest=DEST):
     os.makedirs(os.path.join(out, "meshes"), exist_ok=True)
     for fn in FILES:
         shutil.copyfile(os.path.join(src, fn), os.path.join(out, fn))
+    # the reference's driver (BASELINE config 1), run unmodified against the product by a GPU test
+    shutil.copyfile(os.path.join(ref, "poisson.py"), os.path.join(dest, "poisson.py"))
     for fn in os.listdir(os.path.join(src, "meshes")):
         if fn.endswith(".msh"):
             shutil.copyfile(os.path.join(src, "meshes", fn), os.path.join(out, "meshes", fn))

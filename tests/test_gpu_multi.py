@@ -37,7 +37,7 @@ def _worker(rank, size, port, dims, perturb, N, out, p2p="1"):
         from sempy_b200 import distributed as dd
         from sempy_b200 import mesh as pm
         from sempy_b200.derivative import reference_derivative_matrix
-        from sempy_b200.elliptic import _ax, elliptic_cg, elliptic_pcg
+        from sempy_b200.elliptic import _ax, elliptic_cg, elliptic_pcg, elliptic_pcg_fdm
 
         comm = dd.TorchComm()
         pts, hexes = pm.box_mesh_arrays(*dims, perturb=perturb, seed=2)
@@ -82,6 +82,16 @@ def _worker(rank, size, port, dims, perturb, N, out, p2p="1"):
         if itg != ito:
             xg, _ = elliptic_pcg(m, take(b), tol=0.0, maxit=ito)
         errs["pcg_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
+        # FDM preconditioner (per-element, no exchange of its own; its r.z sum goes over the ranks)
+        S, lam = so.fdm_1d(N)
+        esc = so.fdm_element_scales(*so.element_vertices(pts, hexes))
+        minv = lambda r: so.fdm_apply(r, N, S, lam, esc, dinv)
+        xo, ito = so.elliptic_pcg_fdm(axo, minv, mask, g2l, gs, rmult, b, tol=1e-10, maxit=3000)
+        xg, itg = elliptic_pcg_fdm(m, take(b), tol=1e-10, maxit=3000)
+        errs["fdm_iters"] = float(abs(itg - ito))
+        if itg != ito:
+            xg, _ = elliptic_pcg_fdm(m, take(b), tol=0.0, maxit=ito)
+        errs["fdm_x"] = float(np.abs(xg - take(xo)).max() / np.abs(xo).max())
         # bitwise repeatable across two solves (fixed summation order on every rank and across ranks)
         x1, it1 = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
         x2, it2 = elliptic_pcg(m, take(b), tol=1e-10, maxit=3000)
@@ -116,6 +126,7 @@ def test_four_rank_solver_matches_oracle(tmp_path):
         assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
         assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
         assert e["repeatable"] == 1.0
+        assert e["fdm_iters"] <= 1 and e["fdm_x"] < 1e-10
 
 
 @pytest.mark.parametrize("p2p", ["1", "0"])  # peer-memory transport (default) and the NCCL fallback
@@ -129,3 +140,4 @@ def test_two_rank_solver_matches_oracle(dims, perturb, N, p2p, tmp_path):
         assert e["cg_iters"] <= 1 and e["cg_x"] < 1e-10
         assert e["pcg_iters"] <= 1 and e["pcg_x"] < 1e-10
         assert e["repeatable"] == 1.0
+        assert e["fdm_iters"] <= 1 and e["fdm_x"] < 1e-10

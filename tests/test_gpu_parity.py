@@ -541,3 +541,35 @@ def test_irregular_multiplicities_vs_oracle(N):
     if itg != ito:
         xg, itg = elliptic_pcg(m, b, tol=0.0, maxit=ito)
     assert rel_inf(xg, xo) < 1e-10
+
+
+def test_unmodified_reference_driver_runs_on_the_product(capsys):
+    """BASELINE config 1: the reference's own poisson.py (verbatim copy, oracle/_ref/poisson.py), with
+    `sempy.mesh` / `sempy.elliptic` resolved to the product's modules of the same names.  The script's own
+    asserts (solution against the analytic one, host CG against the "loopy" device CG) must hold."""
+    import os
+    import runpy
+    import sys
+
+    from oracle import make_ref
+
+    script = os.path.join(make_ref.DEST, "poisson.py")
+    if not os.path.isfile(script):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    import sempy_b200
+    import sempy_b200.elliptic
+    import sempy_b200.mesh
+
+    saved = {k: sys.modules.get(k) for k in ("sempy", "sempy.elliptic", "sempy.mesh")}
+    sys.modules.update({"sempy": sempy_b200, "sempy.elliptic": sempy_b200.elliptic, "sempy.mesh": sempy_b200.mesh})
+    try:
+        ns = runpy.run_path(script)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    out = capsys.readouterr().out
+    assert "CG: iters (host/device):" in out and ns["niter"] == ns["niter_loopy"] > 0
+    assert type(ns["mesh"]).__module__ == "sempy_b200.mesh"
