@@ -46,7 +46,8 @@ def f_shared(N):
 # Algorithmic bytes per local node (Ax 64, gather-scatter 20 per shared node, CG vector work)
 BYTES_AX = 64.0            # u 8 + six G 48 + w 8
 BYTES_AX_DIR = 88.0        # + the folded direction update p <- dinv r + beta p: r 8, dinv 8, p written 8
-BYTES_UPDATE = 57.0        # x, p, r, Ap reads 32 + dinv 8 + 1-byte multiplicity + x, r writes 16
+BYTES_UPDATE = 49.0        # r, Ap reads 16 + dinv 8 + 1-byte multiplicity + r write 8, and every SECOND iteration
+                           # p_{k-1}, p_k, x reads 24 + x write 8 (the solution advances two terms at a time)
 
 
 def measured_peaks():
@@ -602,7 +603,7 @@ def run_ours(args):
                      "share_of_step": kern["ax"][0] / ms_total, "gdofs": dof / (ax_ms * 1e-3) / 1e9},
         "kernels": {"ax": kernel_entry("ax", BYTES_AX_DIR, "direction update + Ax + mask + pAp"),
                     "gs": kernel_entry("gs", bytes_gs_long, "in-place gather-scatter of the segments with more than two copies"),
-                    "update": kernel_entry("update", BYTES_UPDATE + 4.0, "x, r update + pairwise gather-scatter (4-byte link) + r.z + scalar step")},
+                    "update": kernel_entry("update", BYTES_UPDATE + 4.0, "r update (x every second iteration) + gather-scatter through 4-byte links + r.z + scalar step")},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * int(dof_all), "d2h_bytes_per_step": 8 * int(dof_all),
                 "ms_per_step": e_s / args.steps * 1e3,

@@ -250,10 +250,7 @@ int64_t semb_launch_count(semb_ctx* ctx);
  * vs NCCL for the halo exchange and the scalar all-reduces.  "gs_pull": 1 (default) / 0,
  * inside semb_cg the two-copy segments of the gather-scatter are summed by the CG
  * update kernel while it streams (only the longer segments keep an in-place pass)
- * vs one in-place pass over all segments.  "edge_buffer": 1 (default) / 0, at N = 7 the
- * operator kernel also writes its edge / vertex values into a dense per-element block
- * that the sums of the longer segments are formed from (dense reads instead of one
- * value per 32-byte sector). */
+ * vs one in-place pass over all segments. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus

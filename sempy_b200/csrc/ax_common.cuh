@@ -26,7 +26,6 @@ struct AxArgs {
   const double* G6;  // (E,6,Np)
   double* w;         // output
   const uint32_t* maskbits;
-  double* eb;        // nullptr, or the compact edge buffer (E, 12*Nq-16): see eb_slot
   CgScalars* s;      // DIR: beta; DOT: pAp
   const int* done;   // nullptr or &s->done
   GridRed red;       // DOT
@@ -48,27 +47,6 @@ template <int DIR>
 __device__ __forceinline__ double dir_update(double p_old, double r, double dinv, double beta) {
   const double z = DIR == 2 ? dinv * r : r;
   return fma(beta, p_old, z);
-}
-
-// Compact "edge buffer".  On a conforming hex mesh the nodes with more than two copies are the element's
-// edge and vertex nodes (12*Nq - 16 of Nq^3).  The operator kernel writes those values of its output a second
-// time into a dense per-element block, so that the gather-scatter of the longer segments reads fully used
-// sectors instead of one 8-byte value per 32-byte sector of the vector.  Slot of node (i, j, k), or -1:
-//   [k = 0 perimeter | k = Nq-1 perimeter | corners (i, j in {0, Nq-1}) of the planes k = 1 .. Nq-2]
-//   perimeter of a plane: row j = 0 (i), row j = Nq-1 (Nq + i), then (i = 0, i = Nq-1) pairs of the rows between.
-__host__ __device__ __forceinline__ int eb_count(int Nq) { return 12 * Nq - 16; }
-__host__ __device__ __forceinline__ int eb_slot(int i, int j, int k, int Nq) {
-  const int L = Nq - 1, P = 4 * Nq - 4;
-  const bool bi = i == 0 || i == L, bj = j == 0 || j == L, bk = k == 0 || k == L;
-  if (bk) {
-    if (!(bi || bj)) return -1;
-    const int base = k == 0 ? 0 : P;
-    if (j == 0) return base + i;
-    if (j == L) return base + Nq + i;
-    return base + 2 * Nq + (j - 1) * 2 + (i == L ? 1 : 0);
-  }
-  if (!(bi && bj)) return -1;
-  return 2 * P + (k - 1) * 4 + (j == L ? 2 : 0) + (i == L ? 1 : 0);
 }
 
 // Host launchers (one per kernel family; defined in the k1_*.cu files).  dir: 0, 1 or 2.

@@ -162,12 +162,6 @@ struct semb_ctx {
   uint32_t* gs_link = nullptr;
   double* gs_sums = nullptr;  // compact sums of the segments with more than two copies
   bool pull_ok = false;       // fewer than 2^30 such segments
-  // compact edge buffer (ax_common.cuh: eb_slot): the operator kernel's second copy of the edge / vertex values
-  // and the ids of the longer segments as positions in it (indexed like gs_ids, shifted by the len-4 class offset)
-  double* eb = nullptr;
-  int32_t* eb_ids = nullptr;
-  int64_t eb_ids_off = 0;
-  bool eb_ok = false;
   double* rmult = nullptr;
   unsigned char* mult = nullptr;  // copy count per node (rmult = 1/mult), read by the CG update kernel
 
@@ -185,7 +179,8 @@ struct semb_ctx {
   semb::CgScalars* scal = nullptr;
   double* hist = nullptr;
   int64_t hist_cap = 0;
-  double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,scratch
+  double* vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r,p,Ap,x,dinv,scratch,p'
+
   double* stage[2] = {nullptr, nullptr};  // pooled staging of HOST vector arguments (never freed per call)
   semb::HostStager hs;                    // pinned ring for pageable HOST arguments
   int* h_pinned = nullptr;  // pinned {done, niter}

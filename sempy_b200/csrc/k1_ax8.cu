@@ -241,13 +241,6 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
     double* we = a.w + e * 512;
     const unsigned long long* mbits = reinterpret_cast<const unsigned long long*>(a.maskbits);
     const int bit = tj * 8 + 2 * ip;
-    // compact copy of the edge / vertex values (eb_slot): rows j = 0, 7 of the planes k = 0, 7 are whole
-    // rows (one 128-bit store per lane), everything else is the i = 0 / i = 7 end of a row
-    double* ebe = (a.eb != nullptr && live) ? a.eb + e * 80 : nullptr;
-    const bool jedge = tj == 0 || tj == 7;
-    const int row_slot = tj == 0 ? 2 * ip : 8 + 2 * ip;    // rows j = 0 / 7 inside a perimeter block
-    const int side_slot = 16 + (tj - 1) * 2;               // rows j = 1..6: (i = 0, i = 7)
-    const int corner = tj == 7 ? 2 : 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const double2 r2 = lds2(A + k * AX8_PS + t_s);
@@ -262,20 +255,6 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
       }
       if (DOT) dot = fma(o.x, uc[k].x, fma(o.y, uc[k].y, dot));
       if (live) *reinterpret_cast<double2*>(we + k * 64 + t_g) = o;
-      if (ebe != nullptr) {
-        if (k == 0 || k == 7) {
-          double* blk = ebe + (k == 0 ? 0 : 28);
-          if (jedge) {
-            *reinterpret_cast<double2*>(blk + row_slot) = o;
-          } else {
-            if (ip == 0) blk[side_slot] = o.x;
-            if (ip == 3) blk[side_slot + 1] = o.y;
-          }
-        } else if (jedge) {
-          if (ip == 0) ebe[56 + (k - 1) * 4 + corner] = o.x;
-          if (ip == 3) ebe[56 + (k - 1) * 4 + corner + 1] = o.y;
-        }
-      }
     }
   }
   if (DOT) {

@@ -7,7 +7,6 @@
 
 #include <cub/cub.cuh>
 
-#include "ax_common.cuh"
 #include "common.cuh"
 
 namespace semb {
@@ -209,23 +208,6 @@ __global__ void seg_emit_kernel(const int32_t* __restrict__ vals, const int64_t*
       const uint32_t lk = 0x40000000u | (uint32_t)(t - lay.b[1]);
       for (int c = 0; c < len; ++c) link[out[c]] = lk;
     }
-  }
-}
-
-// ids of the longer segments re-expressed as positions in the compact edge buffer (ax_common.cuh: eb_slot);
-// info bit 2 is raised when a copy of such a segment is not an edge / vertex node of its element (then the
-// edge buffer is not used)
-__global__ void eb_ids_kernel(const int32_t* __restrict__ ids, int64_t count, int Nq, int32_t* __restrict__ eb_ids,
-                              int* __restrict__ info) {
-  const int Np = Nq * Nq * Nq, NE = eb_count(Nq);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t id = ids[q];
-    const int e = id / Np, node = id - e * Np;
-    const int slot = eb_slot(node % Nq, (node / Nq) % Nq, node / (Nq * Nq), Nq);
-    if (slot < 0) atomicOr(info, 4);
-    const int64_t pos = (int64_t)e * NE + (slot < 0 ? 0 : slot);
-    if (pos > 2147483647LL) atomicOr(info, 4);
-    eb_ids[q] = (int32_t)pos;
   }
 }
 

@@ -518,10 +518,15 @@ __device__ __forceinline__ void cg_update_finish(CgScalars* s, const double* par
 // turned back into the identical double through a small shared-memory table of 1.0/c (a division in
 // the loop costs a MUFU + Newton sequence with a slow-path call per element and made the kernel
 // 16 % slower than reading the 8-byte weights).
-template <bool JACOBI, bool PULL>
+// The solution is advanced every SECOND iteration: x += alpha_{k-1} p_{k-1} + alpha_k p_k (XMODE 2, odd k;
+// the operator kernel alternates between two direction buffers, so p_{k-1} still exists), nothing for even
+// k (XMODE 0); semb_cg applies a pending term after the loop (cg_flush_x_kernel).  Same operations in the
+// same order as one update per iteration (x2 = fma(a1, p1, fma(a0, p0, x0))), so the same bits, for 8 B per
+// node and iteration less traffic (x is read and written half as often).  XMODE 1: one update per iteration.
+template <bool JACOBI, bool PULL, int XMODE>
 __global__ void __launch_bounds__(VEC_NT)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                 const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
+                 const double* __restrict__ p_prev, const double* __restrict__ Ap, const unsigned char* __restrict__ mult, const double* __restrict__ dinv,
                  const uint32_t* __restrict__ link, const double* __restrict__ sums, CgScalars* __restrict__ s, int64_t n,
                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ hist,
                  const LlArgs ll) {
@@ -530,11 +535,13 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
   s_rcp[threadIdx.x] = 1.0 / (double)(threadIdx.x > 0 ? threadIdx.x : 1);  // VEC_NT == 256 entries
   __syncthreads();
   const double alpha = s->rdotr / s->pAp;
+  const double alpha_prev = s->alpha;  // of the previous iteration (XMODE 2)
   double acc = 0.0;
   const int64_t n2 = n >> 1;
   double2* x2 = reinterpret_cast<double2*>(x);
   double2* r2 = reinterpret_cast<double2*>(r);
   const double2* p2 = reinterpret_cast<const double2*>(p);
+  const double2* pp2 = reinterpret_cast<const double2*>(p_prev);
   const double2* a2 = reinterpret_cast<const double2*>(Ap);
   const uchar2* m2 = reinterpret_cast<const uchar2*>(mult);
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
@@ -548,18 +555,26 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
       ov.y = gs_other(Ap, sums, lk.y);
     }
     double2 av = a2[q];
-    const double2 pv = p2[q];
     const uchar2 mc = m2[q];
-    double2 xv = x2[q], rv = r2[q];
+    double2 rv = r2[q];
+    if (XMODE != 0) {
+      const double2 pv = p2[q];
+      double2 xv = x2[q];
+      if (XMODE == 2) {
+        const double2 qv = pp2[q];
+        xv.x = xv.x + alpha_prev * qv.x;
+        xv.y = xv.y + alpha_prev * qv.y;
+      }
+      xv.x = xv.x + alpha * pv.x;
+      xv.y = xv.y + alpha * pv.y;
+      x2[q] = xv;
+    }
     if (PULL) {
       av.x = gs_combine(lk.x, av.x, ov.x);
       av.y = gs_combine(lk.y, av.y, ov.y);
     }
-    xv.x = xv.x + alpha * pv.x;
-    xv.y = xv.y + alpha * pv.y;
     rv.x = rv.x - alpha * av.x;
     rv.y = rv.y - alpha * av.y;
-    x2[q] = xv;
     r2[q] = rv;
     const double wx = s_rcp[mc.x], wy = s_rcp[mc.y];
     if (JACOBI) {
@@ -575,15 +590,26 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
     const int64_t q = n - 1;
     double av = Ap[q];
     if (PULL) av = gs_linked(Ap, sums, link[q], av);
-    const double xv = x[q] + alpha * p[q];
+    if (XMODE != 0) {
+      double xv = x[q];
+      if (XMODE == 2) xv = xv + alpha_prev * p_prev[q];
+      x[q] = xv + alpha * p[q];
+    }
     const double rv = r[q] - alpha * av;
-    x[q] = xv;
     r[q] = rv;
     acc = fma(s_rcp[mult[q]] * rv, JACOBI ? dinv[q] * rv : rv, acc);
   }
   const double sum = block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = sum;
   cg_update_finish(s, partials, ticket, hist, ll);
+}
+
+// x += alpha p for the term that is still pending when the loop ends after an odd number of iterations
+__global__ void __launch_bounds__(VEC_NT)
+cg_flush_x_kernel(double* __restrict__ x, const double* __restrict__ p, const CgScalars* __restrict__ s, int64_t n) {
+  const double alpha = s->alpha;
+  for (int64_t q = (int64_t)blockIdx.x * VEC_NT + threadIdx.x; q < n; q += (int64_t)gridDim.x * VEC_NT)
+    x[q] = x[q] + alpha * p[q];
 }
 
 __global__ void cg_step_scalars_kernel(CgScalars* s, double* hist) {
