@@ -169,11 +169,23 @@ def build_problem(nel, perturb=0.0, comm=None, strong=0):
 
     world = comm.size if comm is not None else 1
     nx, ny, nz = mesh_dims(nel, world, strong)
+    stamps = [("start", time.perf_counter())]
+
+    def stamp(name):
+        torch.cuda.synchronize()
+        stamps.append((name, time.perf_counter()))
+
     m = box_mesh(nx, ny, nz, perturb=perturb, seed=0, comm=comm)
+    stamp("vertex_mesh")
     m.find_physical_coordinates(N_ORDER)
+    stamp("coordinates")
     m.establish_global_numbering()
+    stamp("numbering_gs_halo")
     m.calc_geometric_factors()
+    stamp("geometric_factors")
     m.setup_mask()
+    stamp("mask")
+    m.setup_breakdown = {b[0]: round(b[1] - a[1], 3) for a, b in zip(stamps[:-1], stamps[1:])}
     dev = torch.device("cuda", torch.cuda.current_device())
     X, Y, Z, J = (torch.as_tensor(m.device_array(k), device=dev).reshape(-1) for k in ("x", "y", "z", "jaco"))
     exact = torch.sin(np.pi * X) * torch.sin(np.pi * Y) * torch.sin(np.pi * Z)
@@ -588,7 +600,7 @@ def run_ours(args):
                    "unique_dof_rank0": unique_local,
                    "iterations_per_step": iters_total / args.steps,
                    "cache": "inputs larger than L2 (G alone is %.0f MB per GPU)" % (48.0 * dof / 1e6),
-                   "parallelism": parallelism, "setup_s": t_setup},
+                   "parallelism": parallelism, "setup_s": t_setup, "setup_breakdown_s": getattr(mesh, "setup_breakdown", None)},
         "cg_iters_per_s": iters_total / (ms_total * 1e-3),
         "us_per_iteration": ms_total / max(iters_total, 1) * 1e3,
         "ax_gs": {"gdofs": axgs_gdofs, "ms": axgs_ms, "bytes_per_dof": BYTES_AX + 20.0 * fs, "achieved_gbs": axgs_gbs,

@@ -19,7 +19,10 @@ namespace semb {
 constexpr int AX8_RS = 10;
 constexpr int AX8_PS = 88;
 constexpr int AX8_ARR = 8 * AX8_PS;  // doubles per staged array
-constexpr int AX8_WARPS = 4;         // elements per CTA
+#ifndef AX8_WARPS_N
+#define AX8_WARPS_N 4
+#endif
+constexpr int AX8_WARPS = AX8_WARPS_N;  // elements (= warps) per CTA; 16 warps per SM whatever the split
 constexpr int AX8_SMEM = AX8_WARPS * 2 * AX8_ARR * (int)sizeof(double);
 
 // D is replicated once per phase in the parameter block.  With a single copy the compiler CSEs the
@@ -49,7 +52,7 @@ __device__ __forceinline__ void line8x2(const double (&D)[64], const double (&a)
 }
 
 template <bool MASK, bool DOT, int DIR>
-__global__ void __launch_bounds__(AX8_WARPS * 32, 4)
+__global__ void __launch_bounds__(AX8_WARPS * 32, 16 / AX8_WARPS)
 ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) {
   if (a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) double smem[];
