@@ -186,6 +186,8 @@ def build_problem(nel, perturb=0.0, comm=None, strong=0):
     m.setup_mask()
     stamp("mask")
     m.setup_breakdown = {b[0]: round(b[1] - a[1], 3) for a, b in zip(stamps[:-1], stamps[1:])}
+    if getattr(m, "halo_timings", None):
+        m.setup_breakdown["halo"] = m.halo_timings
     dev = torch.device("cuda", torch.cuda.current_device())
     X, Y, Z, J = (torch.as_tensor(m.device_array(k), device=dev).reshape(-1) for k in ("x", "y", "z", "jaco"))
     exact = torch.sin(np.pi * X) * torch.sin(np.pi * Y) * torch.sin(np.pi * Z)

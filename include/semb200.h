@@ -193,7 +193,10 @@ int semb_cg_generic(int device, int64_t n, semb_apply_fn A, void* A_user, semb_a
  * the interior elements inside semb_cg) and the CG dots with an all-reduce.
  *   semb_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller
  *     broadcasts it (torch.distributed, MPI, a file...).
- *   semb_comm_init: collective over all ranks.
+ *   semb_comm_init: collective over all ranks.  id128 == NULL: no NCCL
+ *     communicator at all (its creation takes seconds on 8 GPUs): the context
+ *     then relies on the peer-memory transport, multiplicities are completed
+ *     inside semb_p2p_attach, and an operation that would need NCCL fails.
  *   semb_set_halo: interface tables of this rank, built by the host-side
  *     partitioner (sempy_b200/distributed.py).  Send entries are grouped by
  *     neighbour in an order both sides share; entry t is the sum of the local

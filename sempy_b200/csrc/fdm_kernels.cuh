@@ -139,4 +139,141 @@ fdm_apply_kernel(const FdmArgs a, const LlArgs ll) {
   if (tid == 0) cg_step_scalars(a.s, a.hist);
 }
 
+// ---------------------------------------------------------------------------
+// Tuned form (interior size M = Nq - 2 >= 2): the three-layout, contract-in-registers scheme of the operator
+// kernels.  Thread (a, b) of an element owns, in turn, the x-line (j = b, k = a), the y-line (i = b, k = a)
+// and the z-column (i = b, j = a) of the M^3 interior block, which lives in ONE padded shared array: every
+// 1-D pass reads a whole line into registers, multiplies by S^T or S with the entries of S coming from the
+// kernel parameter block (uniform registers) and writes the line back in place; forward-z, the eigenvalue
+// scaling and backward-z happen in registers without touching shared memory.  EPB elements share a CTA so
+// that small orders still fill their warps (N = 7: 4 elements x 36 lines).
+// ---------------------------------------------------------------------------
+template <int M>
+struct FdmS {
+  double s[6][M * M];  // one private copy of S per use (see line8x2 in k1_ax8.cu for why)
+  double lam[M];
+};
+
+template <int M, bool TRANSPOSE>
+__device__ __forceinline__ void fdm_line(const double (&S)[M * M], const double (&in)[M], double (&out)[M]) {
+#pragma unroll
+  for (int o = 0; o < M; ++o) {
+    double v = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) v = fma(TRANSPOSE ? S[m * M + o] : S[o * M + m], in[m], v);
+    out[o] = v;
+  }
+}
+
+template <int NQ>
+struct FdmCfg {
+  static constexpr int M = NQ - 2;
+  static constexpr int L = M * M;                                   // lines per direction
+  static constexpr int EPB = (160 / L) > 0 ? (160 / L) : 1;         // elements per CTA
+  static constexpr int NT = EPB * L;
+  static constexpr int RS = (M % 2) ? M : M + 1;                    // odd row stride: conflict-free x-lines
+  static constexpr int PS = M * RS;
+  static constexpr int ARR = M * PS;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(FdmCfg<NQ>::NT)
+fdm_lines_kernel(const FdmArgs a, const LlArgs ll, const __grid_constant__ FdmS<NQ - 2> P, int64_t E) {
+  using C = FdmCfg<NQ>;
+  constexpr int M = C::M, L = C::L, NT = C::NT, RS = C::RS, PS = C::PS, NP = NQ * NQ * NQ;
+  if (a.check_done && a.s->done) return;
+  __shared__ double sm[C::EPB * C::ARR];
+  const int tid = threadIdx.x;
+  const int el = tid / L, l = tid - el * L;
+  const int ta = l / M, tb = l - ta * M;
+  const int64_t e = (int64_t)blockIdx.x * C::EPB + el;
+  const bool live = e < E;
+  double* A = sm + el * C::ARR;
+  const double* re = a.r + e * NP;
+  double* ze = a.z + e * NP;
+  double dot = 0.0;
+  // load: interior -> shared, surface -> point Jacobi
+  if (live) {
+    for (int q = l; q < NP; q += L) {
+      const int i = q % NQ, j = (q / NQ) % NQ, k = q / (NQ * NQ);
+      const bool inner = i > 0 && i < NQ - 1 && j > 0 && j < NQ - 1 && k > 0 && k < NQ - 1;
+      const double rv = re[q];
+      if (inner) {
+        A[(k - 1) * PS + (j - 1) * RS + (i - 1)] = rv;
+      } else {
+        const double zv = a.dinv[e * NP + q] * rv;
+        ze[q] = zv;
+        dot = fma(rv / (double)a.mult[e * NP + q], zv, dot);
+      }
+    }
+  }
+  __syncthreads();
+  double* row = A + ta * PS + tb * RS;   // x-line (j = tb, k = ta)
+  double* col = A + ta * PS + tb;        // y-line (i = tb, k = ta), stride RS
+  double* pil = A + ta * RS + tb;        // z-column (i = tb, j = ta), stride PS
+  double in[M], out[M];
+  // forward x, y
+#pragma unroll
+  for (int q = 0; q < M; ++q) in[q] = row[q];
+  fdm_line<M, true>(P.s[0], in, out);
+#pragma unroll
+  for (int q = 0; q < M; ++q) row[q] = out[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < M; ++q) in[q] = col[q * RS];
+  fdm_line<M, true>(P.s[1], in, out);
+#pragma unroll
+  for (int q = 0; q < M; ++q) col[q * RS] = out[q];
+  __syncthreads();
+  // forward z, eigenvalue scaling, backward z -- all in registers
+#pragma unroll
+  for (int q = 0; q < M; ++q) in[q] = pil[q * PS];
+  fdm_line<M, true>(P.s[2], in, out);
+  {
+    const double ax = live ? a.esc[4 * e + 0] : 1.0, ay = live ? a.esc[4 * e + 1] : 1.0;
+    const double az = live ? a.esc[4 * e + 2] : 1.0, sc = live ? a.esc[4 * e + 3] : 0.0;
+    const double base = ax * P.lam[tb] + ay * P.lam[ta];
+#pragma unroll
+    for (int q = 0; q < M; ++q) out[q] = out[q] * (sc / (base + az * P.lam[q]));
+  }
+  fdm_line<M, false>(P.s[3], out, in);
+#pragma unroll
+  for (int q = 0; q < M; ++q) pil[q * PS] = in[q];
+  __syncthreads();
+  // backward y, x
+#pragma unroll
+  for (int q = 0; q < M; ++q) in[q] = col[q * RS];
+  fdm_line<M, false>(P.s[4], in, out);
+#pragma unroll
+  for (int q = 0; q < M; ++q) col[q * RS] = out[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < M; ++q) in[q] = row[q];
+  fdm_line<M, false>(P.s[5], in, out);
+#pragma unroll
+  for (int q = 0; q < M; ++q) row[q] = out[q];
+  __syncthreads();
+  // store the interior (coalesced) and its part of r.z (interior nodes have one copy: weight 1)
+  if (live) {
+    for (int q = l; q < NP; q += L) {
+      const int i = q % NQ, j = (q / NQ) % NQ, k = q / (NQ * NQ);
+      if (i > 0 && i < NQ - 1 && j > 0 && j < NQ - 1 && k > 0 && k < NQ - 1) {
+        const double zv = A[(k - 1) * PS + (j - 1) * RS + (i - 1)];
+        ze[q] = zv;
+        dot = fma(re[q], zv, dot);
+      }
+    }
+  }
+  const double cta = block_sum_nt<NT>(dot);
+  double total;
+  if (!grid_reduce<NT>(a.red, cta, (int)blockIdx.x, a.ncta, total)) return;
+  if (tid == 0) a.s->rdotr_new = total;
+  if (!a.finish) return;
+  if (ll.nranks > 1) {
+    __syncthreads();
+    ll_allreduce_cta(&a.s->rdotr_new, 1, ll.peers, ll.rank, ll.nranks, ll.seq, ll.ll_error);
+  }
+  if (tid == 0) cg_step_scalars(a.s, a.hist);
+}
+
 }  // namespace semb

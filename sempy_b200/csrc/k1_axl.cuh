@@ -1,5 +1,6 @@
-// K1 for the higher orders (Nq = 9 ... 16, i.e. N = 8 ... 15): the same three-layout, contract-in-registers
-// design as ax8_kernel, with one CTA of Nq^2 threads per element and one line per thread and layout.
+// K1 for every order but N = 7 (Nq = 3 ... 7 and 9 ... 16): the same three-layout, contract-in-registers
+// design as ax8_kernel, with Nq^2 threads per element and one line per thread and layout.  One element per
+// CTA from Nq = 9 up; below that EPB elements share a CTA (Nq = 4: 10 x 16 threads) so that the warps are full.
 //
 //   T: thread (i, j) owns the k-column           -> t-derivative / D^T_t in registers, G applied here
 //   R: thread (j, k) owns the r-line (Nq contiguous values)
@@ -39,8 +40,9 @@ struct AxlCfg {
   static constexpr int RS = V2 ? ((NQ % 4 == 2) ? NQ : NQ + 2) : NQ;
   static constexpr int PS = NQ * RS;
   static constexpr int ARR = NQ * PS;
-  static constexpr int SMEM = 3 * ARR * (int)sizeof(double);
-  static constexpr int NT = NQ * NQ;
+  static constexpr int EPB = (160 / (NQ * NQ)) > 0 ? (160 / (NQ * NQ)) : 1;  // elements per CTA
+  static constexpr int SMEM = EPB * 3 * ARR * (int)sizeof(double);
+  static constexpr int NT = EPB * NQ * NQ;
   // registers and shared memory set the residency: <= 512 threads of 128 registers, <= 227 KB per SM
   static constexpr int BY_REGS = (512 / NT) > 0 ? (512 / NT) : 1;
   static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024) > 0 ? (227 * 1024) / (SMEM + 1024) : 1;
@@ -106,14 +108,18 @@ template <int NQ, bool MASK, bool DOT, int DIR>
 __global__ void __launch_bounds__(AxlCfg<NQ>::NT, AxlCfg<NQ>::MINB)
 axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> Dp) {
   using C = AxlCfg<NQ>;
-  constexpr int NT = C::NT, NP = NQ * NQ * NQ, RS = C::RS, PS = C::PS;
+  constexpr int NT = C::NT, NL = NQ * NQ, NP = NQ * NQ * NQ, RS = C::RS, PS = C::PS;
   if (a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) double smem[];
-  double* A = smem;
-  double* B = smem + C::ARR;
-  double* Cc = smem + 2 * C::ARR;
-  const int tid = threadIdx.x;
-  const int64_t e = a.e0 + blockIdx.x;
+  const int el = C::EPB > 1 ? (int)threadIdx.x / NL : 0;      // element slot of this thread inside the CTA
+  const int tid = C::EPB > 1 ? (int)threadIdx.x - el * NL : (int)threadIdx.x;
+  double* A = smem + el * (3 * C::ARR);
+  double* B = A + C::ARR;
+  double* Cc = A + 2 * C::ARR;
+  // a slot past the end redoes the last element (all threads take part in the barriers) and stores nothing
+  const int64_t e_raw = a.e0 + (int64_t)blockIdx.x * C::EPB + el;
+  const bool live = e_raw < a.e1;
+  const int64_t e = live ? e_raw : a.e1 - 1;
   const double* ue = a.u + e * NP;
   const double* ge = a.G6 + e * (int64_t)(6 * NP);
 
@@ -137,7 +143,7 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   // P1: u -> registers (T) and shared; first plane of G
   double uc[NQ];
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) uc[k] = __ldg(ue + k * NT + t_g);
+  for (int k = 0; k < NQ; ++k) uc[k] = __ldg(ue + k * NL + t_g);
   if (DIR != 0) {
     // CG direction update folded into the load phase: p <- z + beta p, written back and used as u
     const double beta = a.s->beta;
@@ -146,10 +152,10 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
     double* pe = a.p_out + e * NP;
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
-      const double rv = __ldg(re + k * NT + t_g);
-      const double dv = DIR == 2 ? __ldg(de + k * NT + t_g) : 0.0;
+      const double rv = __ldg(re + k * NL + t_g);
+      const double dv = DIR == 2 ? __ldg(de + k * NL + t_g) : 0.0;
       uc[k] = dir_update<DIR>(uc[k], rv, dv, beta);
-      pe[k * NT + t_g] = uc[k];
+      if (live) pe[k * NL + t_g] = uc[k];
     }
   }
   double g[6], gn[6];
@@ -172,7 +178,7 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
     for (int k = 0; k < NQ; ++k) {
       if (k < NQ - 1) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) gn[c] = __ldcs(ge + c * NP + (k + 1) * NT + t_g);
+        for (int c = 0; c < 6; ++c) gn[c] = __ldcs(ge + c * NP + (k + 1) * NL + t_g);
       }
       const double ur = Cc[k * PS + t_s];
       const double us = B[k * PS + t_s];
@@ -209,7 +215,7 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   for (int k = 0; k < NQ; ++k) {
     double o = (A[k * PS + t_s] + B[k * PS + t_s]) + acc[k];
     if (MASK) {
-      const int64_t gi = e * NP + k * NT + t_g;
+      const int64_t gi = e * NP + k * NL + t_g;
       if ((__ldg(a.maskbits + (gi >> 5)) >> (gi & 31)) & 1u) {
         // the reference's dot is p . mask(Ap) (sempy/elliptic.py:49-51): take the masked rows out of
         // (grad u)^T G (grad u) = u . Au.  Rare path (boundary nodes only); u comes back from memory.
@@ -217,12 +223,12 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
         o = 0.0;
       }
     }
-    we[k * NT + t_g] = o;
+    if (live) we[k * NL + t_g] = o;
   }
   if (DOT) {
-    const double cta = block_sum_nt<NT>(dot);
+    const double cta = block_sum_nt<NT>(live ? dot : 0.0);
     double total;
-    if (grid_reduce<NT>(a.red, cta, a.cta_off + (int)blockIdx.x, a.ncta_total, total) && tid == 0) a.s->pAp = total;
+    if (grid_reduce<NT>(a.red, cta, a.cta_off + (int)blockIdx.x, a.ncta_total, total) && threadIdx.x == 0) a.s->pAp = total;
   }
 }
 
@@ -235,7 +241,7 @@ static int launch_axl_t(const AxArgs& a, const DMatL<NQ>& dl, cudaStream_t st, i
     SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, MASK, DOT, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done[device & 63] = true;
   }
-  axl_kernel<NQ, MASK, DOT, DIR><<<(unsigned)(a.e1 - a.e0), Cfg::NT, Cfg::SMEM, st>>>(a, dl);
+  axl_kernel<NQ, MASK, DOT, DIR><<<(unsigned)((a.e1 - a.e0 + Cfg::EPB - 1) / Cfg::EPB), Cfg::NT, Cfg::SMEM, st>>>(a, dl);
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,6 @@
-// K1 for the low orders (Nq = 2 ... 7, N = 1 ... 6): one CTA of Nq^2 threads per element, k-plane sweep
-// with the u column and the D^T_t accumulators in registers.  Correct for every order; not tuned (the
-// BASELINE configs use N = 7 and N = 15, k1_ax8.cu / k1_axl.cuh).  See ax_common.cuh for the fusions.
+// K1 as a plain k-plane sweep, one CTA of Nq^2 threads per element with the u column and the D^T_t
+// accumulators in registers: correct for every order, used for N = 1 (Nq = 2) only -- all other orders go
+// through k1_ax8.cu / k1_axl.cuh.  See ax_common.cuh for the fusions.
 #include <cstring>
 
 #include "ax_common.cuh"
@@ -119,7 +119,9 @@ int launch_ax_generic(int Nq, const AxArgs& a, const DMat& D, bool mask, bool do
 int ax8_num_ctas(int64_t e0, int64_t e1);
 int ax_num_ctas(int Nq, int64_t e0, int64_t e1) {
   if (e1 <= e0) return 0;
-  return Nq == 8 ? ax8_num_ctas(e0, e1) : (int)(e1 - e0);
+  if (Nq == 8) return ax8_num_ctas(e0, e1);
+  const int epb = (Nq >= 3 && 160 / (Nq * Nq) > 0) ? 160 / (Nq * Nq) : 1;  // AxlCfg<NQ>::EPB
+  return (int)((e1 - e0 + epb - 1) / epb);
 }
 
 }  // namespace semb

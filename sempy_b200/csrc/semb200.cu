@@ -147,7 +147,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
   a.e1 = e1;
   a.l2_prefetch = g_ax_l2_prefetch;
   if (c->Nq == 8) return launch_ax8(a, c->D, mask, dot, dir, st, c->device);
-  if (c->Nq >= 9) return launch_axl(c->Nq, a, c->D, mask, dot, dir, st, c->device);
+  if (c->Nq >= 3) return launch_axl(c->Nq, a, c->D, mask, dot, dir, st, c->device);
   return launch_ax_generic(c->Nq, a, c->D, mask, dot, dir, st);
 }
 
@@ -228,6 +228,8 @@ static int halo_gather(semb_ctx* c, const double* x, cudaStream_t st, const int*
 }
 static int halo_exchange(semb_ctx* c, cudaStream_t st) {
   if (c->nb_rank.empty() || use_p2p(c)) return 0;
+  SEMB_CHECK(c->comm != nullptr, "no NCCL communicator (semb_comm_init was called without an id) and the peer-memory "
+                                 "transport is not attached or switched off");
   SEMB_NCCL(GroupStart());
   for (size_t q = 0; q < c->nb_rank.size(); ++q) {
     const int64_t off = c->nb_off[q], cnt = c->nb_off[q + 1] - off;
@@ -271,7 +273,7 @@ static int gs_full(semb_ctx* c, double* x, const int* done) {
   return 0;
 }
 static int allreduce_sum(semb_ctx* c, double* dev, int count) {
-  if (c->comm == nullptr || c->nranks == 1) return 0;
+  if (c->nranks == 1) return 0;
   if (use_p2p(c) && count <= LL_MAXV) {
     c->seq_scalar++;
     c->launch_count++;
@@ -280,6 +282,8 @@ static int allreduce_sum(semb_ctx* c, double* dev, int count) {
     SEMB_CUDA(cudaGetLastError());
     return 0;
   }
+  SEMB_CHECK(c->comm != nullptr, "no NCCL communicator (semb_comm_init was called without an id) and the peer-memory "
+                                 "transport is not attached or switched off");
   SEMB_NCCL(AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
@@ -1251,8 +1255,21 @@ int semb_geom_factors(int device, int Nq, const double* D, const double* w, int6
 // ---- solvers ---------------------------------------------------------------
 namespace semb {
 template <int NQ>
-static int launch_fdm_nq(semb_ctx* c, const FdmArgs& a, const LlArgs& ll) {
-  fdm_apply_kernel<NQ><<<(unsigned)c->E, FDM_NT, 0, c->stream>>>(a, ll);
+static int launch_fdm_nq(semb_ctx* c, FdmArgs a, const LlArgs& ll) {
+  if (NQ >= 4) {
+    // tuned form: lines in registers, S and the eigenvalues from the parameter block
+    constexpr int NQT = NQ >= 4 ? NQ : 4;  // (keeps the M < 2 instantiations out of the tuned kernel)
+    constexpr int M = NQT - 2;
+    using Cfg = FdmCfg<NQT>;
+    FdmS<M> P;
+    for (int u = 0; u < 6; ++u)
+      for (int q = 0; q < M * M; ++q) P.s[u][q] = c->fdm_Sh.d[q];
+    for (int q = 0; q < M; ++q) P.lam[q] = c->fdm_lam[q];
+    a.ncta = (int)((c->E + Cfg::EPB - 1) / Cfg::EPB);
+    fdm_lines_kernel<NQT><<<(unsigned)a.ncta, Cfg::NT, 0, c->stream>>>(a, ll, P, c->E);
+  } else {
+    fdm_apply_kernel<NQ><<<(unsigned)c->E, FDM_NT, 0, c->stream>>>(a, ll);
+  }
   SEMB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1275,7 +1292,7 @@ static int launch_fdm(semb_ctx* c, const double* r, double* z, double* hist, int
   a.check_done = check_done;
   LlArgs ll = ll_args(c, 0);
   ll.nranks = 1;
-  if (finish && c->comm != nullptr && c->nranks > 1 && use_p2p(c)) ll = ll_args(c, ++c->seq_scalar);
+  if (finish && c->nranks > 1 && use_p2p(c)) ll = ll_args(c, ++c->seq_scalar);
   switch (c->Nq) {
 #define SEMB_CASE_F(Q) \
   case Q:              \
@@ -1303,6 +1320,9 @@ int semb_set_fdm(semb_ctx* c, const double* S, const double* lambda, const doubl
     SEMB_CHECK(lambda[q] > 0.0, "semb_set_fdm: eigenvalues must be positive");
     tab[m * m + q] = lambda[q];
   }
+  std::memset(c->fdm_Sh.d, 0, sizeof(c->fdm_Sh.d));
+  for (int q = 0; q < m * m; ++q) c->fdm_Sh.d[q] = S[q];
+  for (int q = 0; q < m; ++q) c->fdm_lam[q] = lambda[q];
   SEMB_TRY(upload(&c->fdm_S, tab.data(), tab.size()));
   SEMB_TRY(upload(&c->fdm_invL, elem_scale, 4 * (size_t)c->E));
   c->fdm_ready = true;
@@ -1356,7 +1376,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   double* two = reinterpret_cast<double*>(c->scal + 1);
   const int grid = vec_grid(n);
   const bool mask = c->have_mask;
-  const bool multi = c->comm != nullptr && c->nranks > 1;
+  const bool multi = c->nranks > 1;
   const bool p2p = multi && use_p2p(c);
   const bool pull = use_pull(c);
 
@@ -1599,12 +1619,14 @@ int semb_comm_unique_id(char* id128) {
 }
 
 int semb_comm_init(semb_ctx* c, int nranks, int rank, const char* id128) {
-  SEMB_CHECK(c && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "semb_comm_init: bad argument");
-  SEMB_CHECK(c->comm == nullptr, "semb_comm_init: communicator already set");
+  SEMB_CHECK(c && nranks >= 1 && rank >= 0 && rank < nranks, "semb_comm_init: bad argument");
+  SEMB_CHECK(c->comm == nullptr && c->comm_stream == nullptr, "semb_comm_init: communicator already set");
   SEMB_TRY(bind_device(c));
-  ncclUniqueId id;
-  std::memcpy(&id, id128, sizeof(id));
-  SEMB_NCCL(CommInitRank(&c->comm, nranks, id, rank));
+  if (id128 != nullptr) {  // NULL: peer-memory transport only, no NCCL communicator (saves its creation time)
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    SEMB_NCCL(CommInitRank(&c->comm, nranks, id, rank));
+  }
   c->nranks = nranks;
   c->rank = rank;
   int prio_lo = 0, prio_hi = 0;
@@ -1621,7 +1643,7 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
                   const int64_t* copy_start, const int32_t* copy_ids, int64_t n_if_elems) {
   SEMB_CHECK(c != nullptr && nneigh >= 0 && n_if >= 0, "semb_set_halo: bad argument");
   SEMB_CHECK(c->have_gs, "semb_set_halo: call semb_set_gather_scatter first");
-  SEMB_CHECK(nneigh == 0 || c->comm != nullptr, "semb_set_halo: call semb_comm_init first");
+  SEMB_CHECK(nneigh == 0 || c->comm_stream != nullptr, "semb_set_halo: call semb_comm_init first");
   SEMB_CHECK(nneigh <= LL_MAXR, "semb_set_halo: too many neighbours");
   SEMB_CHECK(n_if_elems >= 0 && n_if_elems <= c->E, "semb_set_halo: n_if_elems out of range");
   SEMB_TRY(bind_device(c));
@@ -1662,7 +1684,10 @@ int semb_set_halo(semb_ctx* c, int nneigh, const int* nb_rank, const int64_t* nb
   // fallback would leave one side on NCCL while the other spins on peer words): NCCL until all ranks
   // have gone through semb_p2p_alloc / semb_p2p_attach again.
   c->p2p = false;
-  return build_rmult(c);  // multiplicities now count the copies on the other ranks too
+  // multiplicities now count the copies on the other ranks too: over NCCL here, or -- without a NCCL
+  // communicator -- at the end of semb_p2p_attach, once the peer-memory transport can carry the exchange
+  if (c->comm == nullptr && c->nranks > 1) return 0;
+  return build_rmult(c);
 }
 
 static void close_peer_mappings(semb_ctx* c) {
@@ -1674,7 +1699,7 @@ static void close_peer_mappings(semb_ctx* c) {
 int semb_p2p_alloc(semb_ctx* c, int64_t halo_capacity, char* handle64) {
   SEMB_CHECK(c && handle64, "semb_p2p_alloc: NULL argument");
   SEMB_CHECK(halo_capacity >= c->n_send, "semb_p2p_alloc: halo_capacity must cover this rank's interface entries");
-  SEMB_CHECK(c->comm != nullptr && c->have_halo, "semb_p2p_alloc: call semb_comm_init and semb_set_halo first");
+  SEMB_CHECK(c->comm_stream != nullptr && c->have_halo, "semb_p2p_alloc: call semb_comm_init and semb_set_halo first");
   SEMB_CHECK(c->nranks <= LL_MAXR, "semb_p2p_alloc: more ranks than the peer-memory path supports");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   SEMB_TRY(bind_device(c));
@@ -1725,7 +1750,7 @@ int semb_p2p_attach(semb_ctx* c, const char* handles, const int64_t* peer_recv_o
   c->seq_scalar = 0;
   c->seq_halo = 0;
   c->p2p = true;
-  return 0;
+  return build_rmult(c);  // collective: every rank is inside semb_p2p_attach
 }
 
 // ---- memory helpers --------------------------------------------------------

@@ -253,6 +253,7 @@ class Mesh:
         assert len(hexes) > 0 and len(points) > 0
         self.num_global_elements = hexes.shape[0]
         self._halo = None
+        self.halo_timings = {}
         self._shared_vertex = None
         self._n_if_elems = 0
         if self.comm.size > 1:
@@ -496,8 +497,14 @@ class Mesh:
             self._upload_numbering(ctx)
         ctx.have.add("gs")
         if self.comm.size > 1:
+            import time
+
+            t0 = time.perf_counter()
             self._build_halo()
+            t1 = time.perf_counter()
             self._attach_halo(ctx)
+            self.halo_timings = dict(self.halo_timings, build_halo=round(t1 - t0, 3),
+                                     attach_total=round(time.perf_counter() - t1, 3))
 
     def _upload_numbering(self, ctx):
         g2l, gst = self.global_to_local, self.global_start
@@ -567,22 +574,39 @@ class Mesh:
         return self._ctx
 
     def _attach_halo(self, ctx):
-        """NCCL communicator (once per context) and this rank's interface tables."""
+        """Communicator (once per context) and this rank's interface tables."""
+        import time
+
         lib = ctx.lib
+        tick = [time.perf_counter()]
+        marks = {}
+
+        def mark(name):
+            now = time.perf_counter()
+            marks[name] = round(now - tick[0], 3)
+            tick[0] = now
+
+        p2p = os.environ.get("SEMB_P2P", "1") != "0"
         if not getattr(ctx, "comm_ready", False):
-            uid = C.create_string_buffer(128)
-            if self.comm.rank == 0:
-                _capi.check(lib.semb_comm_unique_id(uid))
-            raw = self.comm.bcast(bytes(uid.raw), root=0)
-            _capi.check(lib.semb_comm_init(ctx.handle, self.comm.size, self.comm.rank, raw))
+            if p2p:
+                # peer-memory transport: no NCCL communicator is created at all
+                _capi.check(lib.semb_comm_init(ctx.handle, self.comm.size, self.comm.rank, None))
+            else:
+                uid = C.create_string_buffer(128)
+                if self.comm.rank == 0:
+                    _capi.check(lib.semb_comm_unique_id(uid))
+                raw = self.comm.bcast(bytes(uid.raw), root=0)
+                _capi.check(lib.semb_comm_init(ctx.handle, self.comm.size, self.comm.rank, raw))
             ctx.comm_ready = True
+        mark("comm_init")
         h = self._halo
         keep = [np.ascontiguousarray(h[k]) for k in ("nb_rank", "nb_count", "send_start", "send_ids", "src_start",
                                                       "src_off", "copy_start", "copy_ids")]
         _capi.check(lib.semb_set_halo(ctx.handle, keep[0].size, keep[0].ctypes.data, keep[1].ctypes.data,
                                       keep[2].ctypes.data, keep[3].ctypes.data, h["n_if"], keep[4].ctypes.data,
                                       keep[5].ctypes.data, keep[6].ctypes.data, keep[7].ctypes.data, self._n_if_elems))
-        if os.environ.get("SEMB_P2P", "1") != "0":
+        mark("set_halo")
+        if p2p:
             # peer-memory transport: publish this rank's receive region, map everybody else's
             handle = C.create_string_buffer(64)
             cap = max(self.comm.allgather(int(keep[3].size and h["send_start"].size - 1)))
@@ -591,7 +615,10 @@ class Mesh:
                                             [int(n) for n in h["nb_count"]]))
             peer_off = distributed.peer_receive_offsets([(e[1], e[2]) for e in everyone], self.comm.rank, h["nb_rank"])
             blob = b"".join(e[0] for e in everyone)
+            mark("p2p_alloc_allgather")
             _capi.check(lib.semb_p2p_attach(ctx.handle, blob, peer_off.ctypes.data))
+            mark("p2p_attach")
+        self.halo_timings = marks
 
     def _vector_args(self, x, name):
         """(pointer, mem flag, keep-alive) for an in-place vector argument."""

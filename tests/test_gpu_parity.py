@@ -217,7 +217,8 @@ def test_device_tensors_and_operator():
 
 
 @pytest.mark.parametrize("dims,perturb,N", [((6, 6, 6), 0.0, 7), ((5, 4, 3), 0.3, 7), ((3, 3, 3), 0.3, 15), ((4, 3, 2), 0.3, 10), ((3, 2, 2), 0.25, 1), ((7, 5, 3), 0.2, 2), ((2, 2, 2), 0.3, 5),
-                                            ((3, 2, 2), 0.3, 8), ((2, 3, 2), 0.3, 9), ((2, 2, 3), 0.3, 11), ((2, 2, 2), 0.3, 12), ((2, 2, 2), 0.3, 13), ((2, 2, 2), 0.3, 14)])
+                                            ((3, 2, 2), 0.3, 8), ((2, 3, 2), 0.3, 9), ((2, 2, 3), 0.3, 11), ((2, 2, 2), 0.3, 12), ((2, 2, 2), 0.3, 13), ((2, 2, 2), 0.3, 14),
+                                            ((5, 4, 3), 0.3, 6), ((7, 6, 5), 0.2, 3), ((6, 5, 4), 0.3, 4), ((9, 7, 5), 0.2, 2)])
 def test_generated_meshes_vs_oracle(dims, perturb, N):
     """Seeded inputs on generated boxes (straight and deformed, every kernel
     family: Nq=8 tuned, Nq=16, generic) against the CPU oracle."""
