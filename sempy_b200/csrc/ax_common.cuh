@@ -8,8 +8,8 @@
 //          sempy/iterative.py:83):  p <- z + beta p  with z = r (DIR = 1) or dinv * r (DIR = 2); the new p
 //          is written back and used as u -- the separate direction kernel and one read of p disappear;
 //   MASK : the Dirichlet mask in the epilogue (sempy/mesh.py:487-494);
-//   DOT  : the local p.Ap of sempy/elliptic.py:51, reduced over the whole grid in fixed order by the CTA
-//          that finishes last (reduce.cuh) and stored in s->pAp.
+//   DOT  : the local p.Ap of sempy/elliptic.py:51 as per-warp / per-CTA partial sums; a passenger CTA of the
+//          launch that follows (the gather-scatter) adds them in index order and stores s->pAp.
 // HBM-bound: 64 B per node (u 8 + six G components 48 + w 8; +24 with DIR) against 12*Nq+15 flop.
 #pragma once
 
@@ -53,7 +53,9 @@ __device__ __forceinline__ double dir_update(double p_old, double r, double dinv
 int launch_ax8(const AxArgs& a, const DMat& D, bool mask, bool dot, int dir, cudaStream_t st, int device);
 int launch_axl(int Nq, const AxArgs& a, const DMat& D, bool mask, bool dot, int dir, cudaStream_t st, int device);
 int launch_ax_generic(int Nq, const AxArgs& a, const DMat& D, bool mask, bool dot, int dir, cudaStream_t st);
-// CTAs the launch over [e0, e1) uses (= partials it contributes with DOT)
+// CTAs the launch over [e0, e1) uses; with DOT every CTA writes ax_partials_per_cta(Nq) partial sums of p.Ap
+// to red.part, CTA number cta_off + blockIdx.x first
 int ax_num_ctas(int Nq, int64_t e0, int64_t e1);
+int ax_partials_per_cta(int Nq);
 
 }  // namespace semb

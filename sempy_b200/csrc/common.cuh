@@ -114,7 +114,7 @@ struct HaloPeers {
 // Pageable host memory <-> device through a ring of pinned chunks filled / drained by a few host threads
 // (a plain cudaMemcpy from pageable memory stages through ONE driver thread at ~7 GB/s, measured 37 ms
 // for the 2 x 134 MB of a 32^3-element solve; the ring overlaps several memcpy threads with the DMA).
-constexpr int HS_THREADS = 4;
+constexpr int HS_THREADS = 8;  // at most; hs_copy uses hardware threads / ranks of them, between 2 and 8
 constexpr size_t HS_CHUNK = (size_t)4 << 20;  // bytes per chunk
 struct HostStager {
   bool ready = false;
@@ -175,6 +175,8 @@ struct semb_ctx {
   int64_t partials_cap = 0;
   unsigned int* ticket = nullptr;         // group tickets of the grid reductions (reduce.cuh)
   unsigned int* ticket_update = nullptr;  // the CG update kernel's own ticket (inside the same allocation)
+  double* pass_part = nullptr;            // slice sums / ticket of the p.Ap passengers (vec_kernels.cuh)
+  unsigned int* pass_tick = nullptr;
   int* info = nullptr;                    // 4 device ints for set-up checks
   semb::CgScalars* scal = nullptr;
   double* hist = nullptr;

@@ -244,6 +244,13 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
     double* we = a.w + e * 512;
     const unsigned long long* mbits = reinterpret_cast<const unsigned long long*>(a.maskbits);
     const int bit = tj * 8 + 2 * ip;
+    // all eight mask words first: behind the stores to w the compiler cannot move them (possible aliasing),
+    // and one exposed load latency per plane adds up
+    unsigned long long mw[8];
+    if (MASK) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mw[k] = __ldg(mbits + e * 8 + k);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const double2 r2 = lds2(A + k * AX8_PS + t_s);
@@ -252,7 +259,7 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
       o.x = (r2.x + s2.x) + acc[k].x;
       o.y = (r2.y + s2.y) + acc[k].y;
       if (MASK) {
-        const unsigned long long mb = __ldg(mbits + e * 8 + k) >> bit;
+        const unsigned long long mb = mw[k] >> bit;
         if (mb & 1ull) o.x = 0.0;
         if (mb & 2ull) o.y = 0.0;
       }
@@ -261,14 +268,19 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
     }
   }
   if (DOT) {
-    const double cta = block_sum_nt<AX8_WARPS * 32>(live ? dot : 0.0);
-    double total;
-    if (grid_reduce<AX8_WARPS * 32>(a.red, cta, a.cta_off + (int)blockIdx.x, a.ncta_total, total) && threadIdx.x == 0)
-      a.s->pAp = total;
+    // One partial per warp (lanes added in a fixed shuffle order), no barrier, no atomic: the warps of a CTA
+    // leave independently.  The partials are summed in index order by a passenger CTA of the launch that
+    // follows (gs_fixed_kernel / reduce_partials_kernel) -- the in-kernel grid reduction tried before cost a
+    // fence, a ticket atomic and two barriers per CTA (15 % of this kernel's stall samples, ncu).
+    double v = live ? dot : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) a.red.part[(int64_t)(a.cta_off + (int)blockIdx.x) * AX8_WARPS + warp] = v;
   }
 }
 
 int ax8_num_ctas(int64_t e0, int64_t e1) { return (int)((e1 - e0 + AX8_WARPS - 1) / AX8_WARPS); }
+int ax8_partials_per_cta() { return AX8_WARPS; }
 
 template <bool MASK, bool DOT, int DIR>
 static int launch_ax8_t(const AxArgs& a, const DMat8x& d8, cudaStream_t st, int device) {

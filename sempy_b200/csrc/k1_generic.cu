@@ -82,8 +82,7 @@ ax_generic_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat
   }
   if (DOT) {
     const double cta = block_sum_nt<NT>(dot);
-    double total;
-    if (grid_reduce<NT>(a.red, cta, a.cta_off + (int)blockIdx.x, a.ncta_total, total) && threadIdx.x == 0) a.s->pAp = total;
+    if (threadIdx.x == 0) a.red.part[a.cta_off + (int)blockIdx.x] = cta;  // summed by the next launch's passenger CTA
   }
 }
 
@@ -117,6 +116,9 @@ int launch_ax_generic(int Nq, const AxArgs& a, const DMat& D, bool mask, bool do
 }
 
 int ax8_num_ctas(int64_t e0, int64_t e1);
+int ax8_partials_per_cta();
+// partials of p.Ap that one CTA of the operator launch writes (ax_common.cuh)
+int ax_partials_per_cta(int Nq) { return Nq == 8 ? ax8_partials_per_cta() : 1; }
 int ax_num_ctas(int Nq, int64_t e0, int64_t e1) {
   if (e1 <= e0) return 0;
   if (Nq == 8) return ax8_num_ctas(e0, e1);

@@ -155,7 +155,9 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 // in-place (push) form
 // pull: the two-copy segments are left to the consumer and the longer ones only have their sums formed
 // (compact form, c->gs_sums), nothing is written back to x (pull form, gs_linked)
-static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false) {
+// pass_n > 0: the pass_n partial sums of p.Ap in c->partials are added up (fixed order) into *pass_out by a
+// passenger CTA of the gather-scatter launch, or by a launch of their own when there is nothing to gather
+static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false, int pass_n = 0, double* pass_out = nullptr) {
   const bool skip_pairs = pull;
   double* sums = pull ? c->gs_sums : nullptr;
   ProfScope ps(c, SEMB_K_GS);
@@ -177,7 +179,14 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false)
   const int total_blocks = plan.b2 + plan.b4 + plan.b8;
   if (total_blocks > 0) {
     c->launch_count++;
-    gs_fixed_kernel<<<total_blocks, VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done, sums);
+    GsPassenger pass{pass_n > 0 ? c->partials : nullptr, pass_n, pass_out,
+                     GridRed{c->pass_part, c->pass_part + 32, c->pass_tick}};
+    gs_fixed_kernel<<<total_blocks + (pass_n > 0 ? GS_PASSENGERS : 0), VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done, sums,
+                                                                                            pass);
+    SEMB_CUDA(cudaGetLastError());
+  } else if (pass_n > 0) {
+    c->launch_count++;
+    reduce_partials_kernel<<<1, RED_NT, 0, c->stream>>>(c->partials, pass_n, 0, 1, pass_out, done);
     SEMB_CUDA(cudaGetLastError());
   }
   if (c->gs_var_nseg > 0) {
@@ -322,6 +331,11 @@ static int ensure_partials(semb_ctx* c) {
     SEMB_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int) * (size_t)(groups + 2)));
     c->partials_cap = need;
     c->ticket_update = c->ticket + groups + 1;
+    if (c->pass_part == nullptr) {
+      SEMB_CUDA(cudaMalloc(&c->pass_part, sizeof(double) * 64));
+      SEMB_CUDA(cudaMalloc(&c->pass_tick, sizeof(unsigned int) * 8));
+      SEMB_CUDA(cudaMemset(c->pass_tick, 0, sizeof(unsigned int) * 8));
+    }
   }
   return 0;
 }
@@ -377,9 +391,11 @@ static int hs_copy(semb_ctx* c, void* dev, void* host, size_t bytes, bool to_dev
   HostStager& h = c->hs;
   SEMB_CUDA(cudaEventRecord(h.fence, c->stream));
   const size_t nchunk = (bytes + HS_CHUNK - 1) / HS_CHUNK;
+  // one memcpy thread moves ~10 GB/s, PCIe ~55 GB/s: up to 8 threads, fewer when several ranks share the host
+  const int NTH = std::max(2, std::min(HS_THREADS, (int)std::thread::hardware_concurrency() / std::max(1, c->nranks)));
   cudaError_t errs[HS_THREADS];
   std::thread workers[HS_THREADS];
-  for (int t = 0; t < HS_THREADS; ++t) {
+  for (int t = 0; t < NTH; ++t) {
     errs[t] = cudaSuccess;
     workers[t] = std::thread([&, t]() {
       cudaError_t e = cudaSetDevice(c->device);
@@ -391,7 +407,7 @@ static int hs_copy(semb_ctx* c, void* dev, void* host, size_t bytes, bool to_dev
       size_t off, len;
       if (to_device) {
         int use = 0;
-        for (size_t ch = t; ch < nchunk && e == cudaSuccess; ch += HS_THREADS, ++use) {
+        for (size_t ch = t; ch < nchunk && e == cudaSuccess; ch += NTH, ++use) {
           const int q = use & 1;
           if (use >= 2) e = cudaEventSynchronize(h.ev[t][q]);  // the DMA out of this slot has finished
           if (e != cudaSuccess) break;
@@ -410,9 +426,9 @@ static int hs_copy(semb_ctx* c, void* dev, void* host, size_t bytes, bool to_dev
           e = cudaMemcpyAsync(h.slot[t][0], static_cast<char*>(dev) + off, len, cudaMemcpyDeviceToHost, h.stream[t]);
           if (e == cudaSuccess) e = cudaEventRecord(h.ev[t][0], h.stream[t]);
         }
-        for (; ch < nchunk && e == cudaSuccess; ch += HS_THREADS, ++use) {
+        for (; ch < nchunk && e == cudaSuccess; ch += NTH, ++use) {
           const int q = use & 1;
-          const size_t nxt = ch + HS_THREADS;
+          const size_t nxt = ch + NTH;
           if (nxt < nchunk) {
             size_t o2, l2;
             span(nxt, o2, l2);
@@ -429,8 +445,8 @@ static int hs_copy(semb_ctx* c, void* dev, void* host, size_t bytes, bool to_dev
       errs[t] = e;
     });
   }
-  for (int t = 0; t < HS_THREADS; ++t) workers[t].join();
-  for (int t = 0; t < HS_THREADS; ++t) SEMB_CUDA(errs[t]);
+  for (int t = 0; t < NTH; ++t) workers[t].join();
+  for (int t = 0; t < NTH; ++t) SEMB_CUDA(errs[t]);
   return 0;
 }
 
@@ -606,6 +622,8 @@ int semb_destroy(semb_ctx* c) {
   cudaFree(c->maskbits);
   cudaFree(c->partials);
   cudaFree(c->partials2);
+  cudaFree(c->pass_part);
+  cudaFree(c->pass_tick);
   cudaFree(c->scal);
   cudaFree(c->ticket);
   cudaFree(c->info);
@@ -1400,6 +1418,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   const double* zsrc = fdm ? z : r;
   const int64_t nif = c->have_halo ? c->n_if_elems : 0;
   const int cta1 = ax_num_ctas(c->Nq, 0, nif), cta2 = ax_num_ctas(c->Nq, nif, c->E);
+  const int npart = (cta1 + cta2) * ax_partials_per_cta(c->Nq);  // partial sums of p.Ap per operator application
   int issued = 0;
   int chunk = 1;
   while (true) {
@@ -1439,7 +1458,7 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
           SEMB_TRY(launch_ax(c, p_old, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done, nullptr, false, p));
           SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
         }
-        SEMB_TRY(launch_gs(c, Ap, done, pull));
+        SEMB_TRY(launch_gs(c, Ap, done, pull, npart, &s->pAp));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done, &s->pAp, 1));
       } else if (c->have_halo) {
         // NCCL fallback: same order, the exchange on a second stream
@@ -1453,14 +1472,14 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_CUDA(cudaEventRecord(c->ev_exchanged, c->comm_stream));
         SEMB_TRY(launch_ax(c, p_old, Ap, mask, true, dir, nif, c->E, zsrc, dinv, cta1, cta1 + cta2, done, nullptr, true, p));
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gathered, 0));
-        SEMB_TRY(launch_gs(c, Ap, done, pull));
+        SEMB_TRY(launch_gs(c, Ap, done, pull, npart, &s->pAp));
         // one communicator: its two NCCL operations must not overlap, so the all-reduce follows the exchange
         SEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_exchanged, 0));
         SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
       } else {
         SEMB_TRY(launch_ax(c, p_old, Ap, mask, true, dir, 0, c->E, zsrc, dinv, 0, cta2, done, nullptr, true, p));
-        SEMB_TRY(launch_gs(c, Ap, done, pull));
+        SEMB_TRY(launch_gs(c, Ap, done, pull, npart, &s->pAp));
       }
       // x += alpha p (every second iteration, two terms at once); r -= alpha dssum(Ap); r.z; scalar step
       // (elliptic.py:56-71)

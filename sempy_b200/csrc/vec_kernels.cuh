@@ -86,11 +86,55 @@ struct GsPlan {
 
 // sums (compact form, len-4 and len-8 classes only): segment s of class 4 -> sums[s], of class 8 ->
 // sums[n4 + s]; the irregular rest follows at sums[n4 + n8 + s] (gs_var_kernel).
+// pass.n > 0: the first GS_PASSENGERS blocks of the grid (scheduled first; as the last blocks they would start
+// when the others are finishing and put their sums on the critical path) are passengers that add the
+// pass.n partial sums of p.Ap left by the operator launch and store the total in *pass.out: every passenger
+// sums a fixed slice (16 loads in flight per thread: one CTA alone is latency-bound at ~0.4 ns per partial,
+// 100 us for the 262 144 partials of a 64^3-element mesh), the one that finishes last adds the slice sums
+// in index order (reduce.cuh).
+constexpr int GS_PASSENGERS = 16;
+struct GsPassenger {
+  const double* part;  // nullptr: no passengers
+  int n;
+  double* out;
+  GridRed red;         // scratch of the slice reduction (not the array `part` points into)
+};
+
+__device__ __forceinline__ void gs_passenger(const GsPassenger& pass, int slice) {
+  constexpr int PU = 16;
+  const int len = (pass.n + GS_PASSENGERS - 1) / GS_PASSENGERS;
+  const int lo = slice * len, hi = min(pass.n, lo + len);
+  double v[PU];
+#pragma unroll
+  for (int u = 0; u < PU; ++u) v[u] = 0.0;
+  int t = lo + threadIdx.x;
+  for (; t + (PU - 1) * VEC_NT < hi; t += PU * VEC_NT) {
+#pragma unroll
+    for (int u = 0; u < PU; ++u) v[u] += __ldcg(pass.part + t + u * VEC_NT);
+  }
+  for (; t < hi; t += VEC_NT) v[0] += __ldcg(pass.part + t);
+#pragma unroll
+  for (int w = PU / 2; w > 0; w >>= 1) {
+#pragma unroll
+    for (int u = 0; u < w; ++u) v[u] += v[u + w];
+  }
+  const double mine = block_sum_nt<VEC_NT>(v[0]);
+  double total;
+  if (grid_reduce<VEC_NT>(pass.red, mine, slice, GS_PASSENGERS, total) && threadIdx.x == 0) *pass.out = total;
+}
+
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
-                const int* __restrict__ done, double* __restrict__ sums) {
+                const int* __restrict__ done, double* __restrict__ sums, const GsPassenger pass) {
   if (done != nullptr && *done) return;
   int b = blockIdx.x;
+  if (pass.part != nullptr) {
+    b -= GS_PASSENGERS;
+    if (b < 0) {
+      gs_passenger(pass, b + GS_PASSENGERS);
+      return;
+    }
+  }
   if (b < plan.b2) {
     const int64_t stride = (int64_t)plan.b2 * VEC_NT;
     for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += 4 * stride)
