@@ -492,7 +492,7 @@ def run_ours(args):
     # ---- end-to-end arm: host arrays through the reference-facing call -------------
     # (a) the drop-in call exactly as the reference's callers make it: a pageable NumPy b, a fresh NumPy x
     b_host = b_dev.cpu().numpy()
-    for _ in range(1):
+    for _ in range(2):  # two results alive at a time: both pinned blocks of the result pool exist after this
         x_host, _ = elliptic_pcg(mesh, b_host, tol=TOL, maxit=MAXIT)
     sync_all()
     t0 = time.perf_counter()
