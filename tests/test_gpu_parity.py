@@ -574,3 +574,52 @@ def test_unmodified_reference_driver_runs_on_the_product(capsys):
     out = capsys.readouterr().out
     assert "CG: iters (host/device):" in out and ns["niter"] == ns["niter_loopy"] > 0
     assert type(ns["mesh"]).__module__ == "sempy_b200.mesh"
+
+
+def test_misaligned_device_vectors_are_refused():
+    """The vector kernels use 128-bit accesses: a contiguous CUDA view with an odd element offset must raise
+    (ValueError from the Python checks, RuntimeError from the C ABI) instead of faulting inside a kernel."""
+    torch = pytest.importorskip("torch")
+    from sempy_b200.elliptic import elliptic_ax, elliptic_cg
+
+    g = load_golden("box008_N7")
+    m = golden_mesh(g)
+    n = g["p"].size
+    base = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+    view = base[1:]
+    view.copy_(torch.from_numpy(g["p"]))
+    assert view.is_contiguous() and view.data_ptr() % 16 == 8
+    with pytest.raises(ValueError):
+        m.dssum(view)
+    with pytest.raises(ValueError):
+        m.apply_mask(view)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        elliptic_ax(m, view)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        elliptic_cg(m, view, tol=1e-8, maxit=5)
+    # the context is still usable afterwards (no sticky CUDA error)
+    ok = elliptic_ax(m, torch.from_numpy(g["p"]).cuda())
+    assert rel_inf(ok.cpu().numpy(), g["ax_raw"]) <= AX_TOL
+
+
+def test_setup_order_and_missing_pieces_raise():
+    """Calls before their set-up step fail loudly, as the reference's attribute errors would."""
+    from sempy_b200.elliptic import elliptic_ax, elliptic_cg
+    from sempy_b200.mesh import box_mesh
+
+    m = box_mesh(2, 2, 2)
+    with pytest.raises(RuntimeError):
+        m.dssum(np.zeros(8))  # no order yet
+    m.find_physical_coordinates(3)
+    n = m.get_num_elems() * m.Np
+    with pytest.raises(RuntimeError, match="establish_global_numbering"):
+        m.dssum(np.zeros(n))
+    with pytest.raises(RuntimeError, match="calc_geometric_factors"):
+        elliptic_ax(m, np.zeros(n))
+    m.establish_global_numbering()
+    m.calc_geometric_factors()
+    with pytest.raises(RuntimeError, match="setup_mask"):
+        m.apply_mask(np.zeros(n))
+    b = m.dssum(np.random.default_rng(1).standard_normal(n))
+    x, it = elliptic_cg(m, b, tol=1e-8, maxit=3)  # the mask is optional for the solver
+    assert it == 3 and np.isfinite(x).all()
