@@ -59,30 +59,6 @@ class TorchComm:
         self._dist.broadcast_object_list(box, src=root, group=self._group)
         return box[0]
 
-    def exchange(self, sends):
-        """Point-to-point exchange of float64 arrays of shape (k, 3): ``sends`` maps destination rank ->
-        array; returns source rank -> array.  Collective (every rank calls it, possibly with nothing to send)."""
-        import torch
-
-        dist = self._dist
-        counts = self.allgather({int(q): int(a.shape[0]) for q, a in sends.items()})
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self._group) == "nccl" else torch.device("cpu")
-        ops, bufs, keep = [], {}, []
-        for q, a in sends.items():
-            if a.shape[0]:
-                t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
-                keep.append(t)
-                ops.append(dist.P2POp(dist.isend, t, int(q), group=self._group))
-        for q in range(self.size):
-            k = counts[q].get(self.rank, 0)
-            if k:
-                bufs[q] = torch.empty((k, 3), dtype=torch.float64, device=dev)
-                ops.append(dist.P2POp(dist.irecv, bufs[q], q, group=self._group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return {q: t.cpu().numpy() for q, t in bufs.items()}
-
 
 def slab_ranges(num_elems, nranks):
     """Contiguous, balanced element ranges [(lo, hi), ...]."""
@@ -159,23 +135,7 @@ def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     uid, first, ncopy_all = np.unique(cgid, return_index=True, return_counts=True)
     rep = cpos[first]                                                         # one local copy of each
     mine = np.stack([x[rep], y[rep], z[rep]], axis=1)
-    if hasattr(comm, "exchange"):
-        # neighbours only: all-gather the bounding boxes of the candidates (tiny), then send every rank whose box
-        # meets mine the candidates of mine that lie inside it -- both sides of an interface still see every
-        # member of the groups they take part in
-        box = (mine.min(axis=0) - 1e-5, mine.max(axis=0) + 1e-5) if mine.shape[0] else None
-        boxes = comm.allgather(box)
-        sends = {}
-        for q, bq in enumerate(boxes):
-            if q == rank or bq is None or box is None:
-                continue
-            if np.all(bq[0] <= box[1]) and np.all(box[0] <= bq[1]):
-                inside = np.all((mine >= bq[0]) & (mine <= bq[1]), axis=1)
-                sends[q] = mine[inside]
-        got = comm.exchange(sends)
-        parts = [mine if q == rank else got.get(q, np.zeros((0, 3))) for q in range(size)]
-    else:
-        parts = comm.allgather(mine)
+    parts = comm.allgather(mine)
     counts = np.array([p.shape[0] for p in parts], dtype=np.int64)
     offs = np.concatenate(([0], np.cumsum(counts)))
     allc = np.concatenate(parts, axis=0)
