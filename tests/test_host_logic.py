@@ -125,3 +125,35 @@ def test_bundled_meshes_equal_the_reference_fixtures():
         if os.path.exists(ref):
             rp, rh, _ = pm.read_gmsh22(ref)
             assert np.array_equal(pts, rp) and np.array_equal(hexes, rh)
+
+
+@pytest.mark.parametrize("N", [2, 3, 7, 10, 15])
+def test_fdm_host_setup_matches_the_oracle(N):
+    """sempy_b200.fdm (symmetric eigen-solve on the B-scaled interior matrix) against the oracle's restatement
+    of the reference sketch (scipy.linalg.eigh(A, B), example.py:92-100): same eigenvalues, the same
+    preconditioner matrix S diag(1/lambda) S^T (eigenvectors are only defined up to sign), S^T B S = I."""
+    from oracle import sem_oracle as so
+    from sempy_b200 import fdm
+    from sempy_b200.mass import reference_mass_matrix_1d
+
+    S, lam = fdm.fdm_1d(N)
+    So, lamo = so.fdm_1d(N)
+    assert np.allclose(lam, lamo, rtol=1e-11) and (lam > 0).all()
+    P, Po = S @ np.diag(1.0 / lam) @ S.T, So @ np.diag(1.0 / lamo) @ So.T
+    assert np.abs(P - Po).max() <= 1e-11 * np.abs(Po).max()
+    B = reference_mass_matrix_1d(N)[1:-1, 1:-1]
+    assert np.abs(S.T @ B @ S - np.eye(N - 1)).max() < 1e-12
+
+
+def test_fdm_element_scales():
+    from oracle import sem_oracle as so
+    from sempy_b200 import fdm, mesh as pm
+
+    pts, hexes = pm.box_mesh_arrays(3, 2, 4, perturb=0.3, seed=5)
+    vx, vy, vz = pts[hexes, 0], pts[hexes, 1], pts[hexes, 2]
+    got = fdm.element_scales(vx, vy, vz)
+    assert np.allclose(got, so.fdm_element_scales(vx, vy, vz), rtol=1e-13)
+    # a straight 3 x 2 x 4 box: a = (2 / h)^2 per direction, scale = 8 / volume
+    pts, hexes = pm.box_mesh_arrays(3, 2, 4)
+    sc = fdm.element_scales(pts[hexes, 0], pts[hexes, 1], pts[hexes, 2])
+    assert np.allclose(sc, [[36.0, 16.0, 64.0, 8.0 * 24.0]] * 24)
