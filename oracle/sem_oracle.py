@@ -14,6 +14,10 @@ below against those files.  The one boundary that no reference test pins
 directly is ``gslib_wrapper.GS.gs`` (third-party, absent, version not stated by
 the reference): only the summed value is defined there, not the summation
 order, so ``gather_scatter`` is pinned to 1 ulp-level agreement, not bitwise.
+The FDM functions at the end (``fdm_*``, ``fast_kron``, a "next" row of the scope) are the exception --
+parity UNPINNED against reference outputs: the reference's ``example.py`` does not run (undefined names
+at ``:33,36,49``), so they are pinned to the properties the sketch defines (dense Kronecker product,
+exact inverse of the interior blocks on straight elements; ``tests/test_oracle_golden.py``).
 
 Each function cites the reference lines it follows (paths relative to the
 reference checkout).
