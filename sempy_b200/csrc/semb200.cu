@@ -173,9 +173,9 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false,
     const int64_t want = (nseg + (int64_t)VEC_NT * per_thread - 1) / ((int64_t)VEC_NT * per_thread);
     return (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8);
   };
-  plan.b2 = blocks_for(plan.n2, 4);
-  plan.b4 = blocks_for(plan.n4, 2);
-  plan.b8 = blocks_for(plan.n8, 1);
+  plan.b2 = blocks_for(plan.n2, GS_U2);
+  plan.b4 = blocks_for(plan.n4, GS_U4);
+  plan.b8 = blocks_for(plan.n8, GS_U8);
   const int total_blocks = plan.b2 + plan.b4 + plan.b8;
   if (total_blocks > 0) {
     c->launch_count++;

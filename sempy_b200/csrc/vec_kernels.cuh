@@ -78,6 +78,12 @@ __device__ __forceinline__ void gs_segments(double* __restrict__ x, const int32_
 // All fixed-length classes in ONE launch: the grid is split into three block ranges (len 2 | 4 | 8), so
 // a block works on one class only.  (Three launches cost two extra drain/launch bubbles and a nearly
 // empty len-8 grid: 8.8 us for 0.13 waves, profiles/r01_summary.md.)
+// segments per thread and trip (memory-level parallelism of the latency-bound pass)
+#ifndef GS_U2
+#define GS_U2 4
+#define GS_U4 2
+#define GS_U8 1
+#endif
 struct GsPlan {
   int64_t n2, n4, n8;        // segments per class
   int64_t off2, off4, off8;  // start of each class in ids (multiples of 4 ints)
@@ -137,21 +143,21 @@ gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const G
   }
   if (b < plan.b2) {
     const int64_t stride = (int64_t)plan.b2 * VEC_NT;
-    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += 4 * stride)
-      gs_segments<2, 4>(x, ids + plan.off2, t, stride, plan.n2);
+    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n2; t += GS_U2 * stride)
+      gs_segments<2, GS_U2>(x, ids + plan.off2, t, stride, plan.n2);
     return;
   }
   b -= plan.b2;
   if (b < plan.b4) {
     const int64_t stride = (int64_t)plan.b4 * VEC_NT;
-    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n4; t += 2 * stride)
-      gs_segments<4, 2>(x, ids + plan.off4, t, stride, plan.n4, sums);
+    for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n4; t += GS_U4 * stride)
+      gs_segments<4, GS_U4>(x, ids + plan.off4, t, stride, plan.n4, sums);
     return;
   }
   b -= plan.b4;
   const int64_t stride = (int64_t)plan.b8 * VEC_NT;
-  for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n8; t += stride)
-    gs_segments<8, 1>(x, ids + plan.off8, t, stride, plan.n8, sums != nullptr ? sums + plan.n4 : nullptr);
+  for (int64_t t = (int64_t)b * VEC_NT + threadIdx.x; t < plan.n8; t += GS_U8 * stride)
+    gs_segments<8, GS_U8>(x, ids + plan.off8, t, stride, plan.n8, sums != nullptr ? sums + plan.n4 : nullptr);
 }
 
 // Segments of any other length (unstructured meshes): CSR offsets.
