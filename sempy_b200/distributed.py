@@ -118,7 +118,7 @@ def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     first): every copy of an interface node lies in such an element and is itself a candidate, so the
     interior of a slab never has to leave the device.  cand: candidate mask; global_id: this rank's
     LOCAL numbering; numbering: the coordinate-numbering function (the reference's rule).
-    Collective: one allgather of the candidates' coordinates.
+    Collective: one allgather of the candidates' coordinates ((3, n) arrays).
     """
     rank, size = comm.rank, comm.size
     empty = dict(nb_rank=np.zeros(0, np.int32), nb_count=np.zeros(0, np.int64), send_start=np.zeros(1, np.int64),
@@ -129,51 +129,66 @@ def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     x, y, z = xe.reshape(-1), ye.reshape(-1), ze.reshape(-1)
     # candidate copies grouped by local id, ascending local index inside a group (fixed summation order)
     cpos = np.flatnonzero(cand.reshape(-1))
-    cgid = global_id.reshape(-1)[cpos].astype(np.int64)
+    cgid = global_id.reshape(-1)[cpos]
     by_id = np.argsort(cgid, kind="stable")
     cpos, cgid = cpos[by_id], cgid[by_id]
-    uid, first, ncopy_all = np.unique(cgid, return_index=True, return_counts=True)
+    first = np.flatnonzero(np.concatenate(([True], cgid[1:] != cgid[:-1]))) if cgid.size else np.zeros(0, np.int64)
+    ncopy_all = np.diff(np.concatenate((first, [cgid.size])))
     rep = cpos[first]                                                         # one local copy of each
-    mine = np.stack([x[rep], y[rep], z[rep]], axis=1)
+    mine = np.stack([x[rep], y[rep], z[rep]])                                  # (3, n): coordinate-major
     parts = comm.allgather(mine)
-    counts = np.array([p.shape[0] for p in parts], dtype=np.int64)
-    offs = np.concatenate(([0], np.cumsum(counts)))
-    allc = np.concatenate(parts, axis=0)
-    if allc.shape[0] == 0 or mine.shape[0] == 0:
+    if mine.shape[1] == 0:
         return empty
-    owner = np.repeat(np.arange(size), counts)
-    pos = np.arange(allc.shape[0]) - offs[owner]
     # Only points inside the bounding box of MY candidates can share a node with me (the matching
-    # tolerance is 1e-6 in distance): drop the rest before sorting.  Every member of each of my groups
-    # survives on every rank that owns one of them, and the order of two groups is decided by their own
-    # members' coordinates, so both sides of an interface still list their shared nodes in the same order.
-    lo, hi = mine.min(axis=0) - 1e-5, mine.max(axis=0) + 1e-5
-    near = np.all((allc >= lo) & (allc <= hi), axis=1)
-    allc, owner, pos = allc[near], owner[near], pos[near]
+    # tolerance is 1e-6 in distance): drop the rest before sorting -- whole ranks first (with slabs all but
+    # the two neighbours), then point by point.  Every member of each of my groups survives on every rank
+    # that owns one of them, and the order of two groups is decided by their own members' coordinates, so
+    # both sides of an interface still list their shared nodes in the same order.
+    lo, hi = mine.min(axis=1) - 1e-5, mine.max(axis=1) + 1e-5
+    kept, owner, pos = [], [], []
+    for q, part in enumerate(parts):
+        if part.shape[1] == 0:
+            continue
+        if q == rank:
+            sel = np.arange(part.shape[1])
+        else:
+            if np.any(part.min(axis=1) > hi) or np.any(part.max(axis=1) < lo):
+                continue
+            near = (part[0] >= lo[0]) & (part[0] <= hi[0])
+            for a in (1, 2):
+                near &= part[a] >= lo[a]
+                near &= part[a] <= hi[a]
+            sel = np.flatnonzero(near)
+            part = part[:, sel]
+        kept.append(part)
+        owner.append(np.full(sel.size, q, dtype=np.int64))
+        pos.append(sel)
+    allc, owner, pos = np.concatenate(kept, axis=1), np.concatenate(owner), np.concatenate(pos)
     # the reference's rule on the union
-    gid_all, _, gs_all = numbering(np.ascontiguousarray(allc[:, 0])[None, :], np.ascontiguousarray(allc[:, 1])[None, :],
-                                   np.ascontiguousarray(allc[:, 2])[None, :])
+    gid_all, _, gs_all = numbering(allc[0:1], allc[1:2], allc[2:3])
     grp = gid_all.reshape(-1).astype(np.int64) - 1
+    ngrp = int(gs_all.size - 1)
     multi = np.diff(gs_all)[grp] >= 2
     grp, owner, pos = grp[multi], owner[multi], pos[multi]
     # a group must not hold two entries of one rank (the local numbering already merged those)
-    key = grp * size + owner
-    if np.unique(key).size != key.size:
+    if grp.size and np.bincount(grp * size + owner).max() > 1:
         raise RuntimeError("interface matching: two local nodes of one rank fell into the same global node")
     me = owner == rank
     order = np.argsort(grp[me], kind="stable")
     g_mine = grp[me][order]                     # my interface nodes, ascending group id (canonical order)
-    idx_mine = pos[me][order]                   # their rows in uid / first / ncopy_all
+    idx_mine = pos[me][order]                   # their rows in first / ncopy_all
     n_if = g_mine.size
     if n_if == 0:
         return empty
     # the other members of my groups: (neighbour rank, group)
-    other = (~me) & np.isin(grp, g_mine)
+    node_of_grp = np.full(ngrp, -1, dtype=np.int64)
+    node_of_grp[g_mine] = np.arange(n_if)
+    other = (~me) & (node_of_grp[grp] >= 0)
     m_o, g_o = owner[other], grp[other]
-    lay = np.lexsort((g_o, m_o))                # send layout: by neighbour, then by group id
+    lay = np.argsort(m_o * ngrp + g_o, kind="stable")   # send layout: by neighbour, then by group id
     m_o, g_o = m_o[lay], g_o[lay]
     n_send = m_o.size
-    node_of = np.searchsorted(g_mine, g_o)      # my node behind each send entry
+    node_of = node_of_grp[g_o]                  # my node behind each send entry
     nb_rank, nb_count = np.unique(m_o, return_counts=True)
     # local copies per interface node (ascending local index)
     lo = first[idx_mine]
@@ -188,11 +203,11 @@ def build_halo(comm, xe, ye, ze, cand, global_id, numbering):
     send_ids = copy_ids[sflat]
     # sources per node in ascending rank order: own partial (first send entry of the node) + received ones
     own_off = np.full(n_if, n_send, dtype=np.int64)
-    np.minimum.at(own_off, node_of, np.arange(n_send))
+    own_off[node_of[::-1]] = np.arange(n_send - 1, -1, -1)   # written back to front: the smallest entry wins
     s_node = np.concatenate((np.arange(n_if), node_of))
     s_rank = np.concatenate((np.full(n_if, rank), m_o))
     s_off = np.concatenate((own_off, n_send + np.arange(n_send)))
-    so = np.lexsort((s_rank, s_node))
+    so = np.argsort(s_node * size + s_rank, kind="stable")
     src_off = s_off[so]
     src_start = np.concatenate(([0], np.cumsum(np.bincount(s_node, minlength=n_if))))
     return dict(nb_rank=nb_rank.astype(np.int32), nb_count=nb_count.astype(np.int64),
