@@ -12,6 +12,8 @@ from sempy_b200 import _capi  # noqa: E402
 from sempy_b200.elliptic import _ax, elliptic_pcg  # noqa: E402
 from sempy_b200.mesh import box_mesh  # noqa: E402
 
+if os.environ.get("SEMB_LIB"):  # a library variant built by scripts/build_variant.sh
+    _capi._LIB_PATH = os.path.abspath(os.environ["SEMB_LIB"])
 for kv in os.environ.get("KNOBS", "").split(","):
     if kv:
         _capi.check(_capi.lib().semb_set_tuning(kv.split("=")[0].encode(), int(kv.split("=")[1])))
@@ -42,11 +44,13 @@ for N, nel in cases:
         best = min(best, ev0.elapsed_time(ev1) / 10)
     x, it = elliptic_pcg(m, p, tol=1e-30, maxit=30)
     torch.cuda.synchronize()
-    ev0.record()
-    x, it = elliptic_pcg(m, p, tol=1e-30, maxit=30)
-    ev1.record()
-    torch.cuda.synchronize()
-    pcg = ev0.elapsed_time(ev1) / it
+    pcg = 1e9
+    for rep in range(4):
+        ev0.record()
+        x, it = elliptic_pcg(m, p, tol=1e-30, maxit=30)
+        ev1.record()
+        torch.cuda.synchronize()
+        pcg = min(pcg, ev0.elapsed_time(ev1) / it)
     fs = 1 - ((N - 1) / (N + 1)) ** 3
     print(f"N={N:2d} nel={nel:3d} nodes={n/1e6:6.2f}M setup {tset:5.1f}s | Ax {best*1e3:8.1f} us {n/best/1e6:7.2f} GDOF/s "
           f"{64*n/best/1e6/6543.4*100:5.1f}% HBM | PCG iter {pcg*1e3:8.1f} us {n/pcg/1e6:6.2f} GDOF/s "

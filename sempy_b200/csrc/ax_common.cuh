@@ -42,6 +42,20 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
+// Output stores (w, and p with DIR): AX_ST_CS = 1 marks them evict-first -- by the time another kernel reads
+// them the rest of this launch (>= 1 GB at the bench sizes) has passed through the L2.
+#ifndef AX_ST_CS
+#define AX_ST_CS 0
+#endif
+__device__ __forceinline__ void st_out(double* p, double v) {
+  if (AX_ST_CS) __stcs(p, v);
+  else *p = v;
+}
+__device__ __forceinline__ void st_out2(double* p, double2 v) {
+  if (AX_ST_CS) __stcs(reinterpret_cast<double2*>(p), v);
+  else *reinterpret_cast<double2*>(p) = v;
+}
+
 // p <- z + beta p for one value (the same expression in every kernel that forms it)
 template <int DIR>
 __device__ __forceinline__ double dir_update(double p_old, double r, double dinv, double beta) {

@@ -22,6 +22,15 @@ constexpr int AX8_ARR = 8 * AX8_PS;  // doubles per staged array
 #ifndef AX8_WARPS_N
 #define AX8_WARPS_N 4
 #endif
+// Where the L2 prefetch of G is issued (build knob, see k1_axl.cuh): 0 = first thing, 1 = behind the loads of P1
+// (default: 183.2 -> 182.4 us plain, 421 -> 415 us per PCG iteration at 32^3), 2 = after P1.
+#ifndef AX_PF_POS
+#define AX_PF_POS -1
+#endif
+constexpr int AX8_PF = AX_PF_POS < 0 ? 1 : (AX_PF_POS == 3 ? 1 : AX_PF_POS);
+#ifndef AX8_GPD
+#define AX8_GPD 1  // planes of G in flight ahead of the plane being used (build knob)
+#endif
 constexpr int AX8_WARPS = AX8_WARPS_N;  // elements (= warps) per CTA; 16 warps per SM whatever the split
 constexpr int AX8_SMEM = AX8_WARPS * 2 * AX8_ARR * (int)sizeof(double);
 
@@ -81,8 +90,11 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
     // the HBM peak).  One lane therefore asks the L2 for the element's whole 24 KB block of G up
     // front (TMA-style bulk prefetch, no registers, no shared memory); the plane loads then hit L2.
     // Measured 206 -> 178 us per launch at 32^3 elements (92 % of the measured HBM peak).
-    if (a.l2_prefetch && lane == 0)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge), "r"(6 * 512 * 8) : "memory");
+    auto prefetch_g = [&]() {
+      if (a.l2_prefetch && lane == 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge), "r"(6 * 512 * 8) : "memory");
+    };
+    if (AX8_PF == 0) prefetch_g();
 
     // P1: u -> registers (T) and shared; with DIR the direction update happens here
     double2 uc[8];
@@ -96,13 +108,17 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
 #pragma unroll
       for (int k = 0; k < 8; ++k) rv[k] = __ldg(reinterpret_cast<const double2*>(re + k * 64 + t_g));
       if (DIR == 2) {
+        double2 dv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dv[k] = __ldg(reinterpret_cast<const double2*>(de + k * 64 + t_g));
+        if (AX8_PF == 1) prefetch_g();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const double2 dv = __ldg(reinterpret_cast<const double2*>(de + k * 64 + t_g));
-          uc[k].x = dir_update<2>(uc[k].x, rv[k].x, dv.x, beta);
-          uc[k].y = dir_update<2>(uc[k].y, rv[k].y, dv.y, beta);
+          uc[k].x = dir_update<2>(uc[k].x, rv[k].x, dv[k].x, beta);
+          uc[k].y = dir_update<2>(uc[k].y, rv[k].y, dv[k].y, beta);
         }
       } else {
+        if (AX8_PF == 1) prefetch_g();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uc[k].x = dir_update<1>(uc[k].x, rv[k].x, 0.0, beta);
@@ -112,13 +128,16 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
       if (live) {
         double* pe = a.p_out + e * 512;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<double2*>(pe + k * 64 + t_g) = uc[k];
+        for (int k = 0; k < 8; ++k) st_out2(pe + k * 64 + t_g, uc[k]);
       }
     }
-    // first plane of G requested now so it overlaps the r/s passes
-    double2 g[6];
+    if (AX8_PF == 1 && DIR == 0) prefetch_g();
+    if (AX8_PF == 2) prefetch_g();
+    // first plane of G requested now so it overlaps the r/s passes; ring of AX8_GPD + 1 register sets
+    constexpr int GPD = AX8_GPD, GS = GPD + 1;
+    double2 g[GS][6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) g[c] = ld_stream2(ge + c * 512 + t_g);
+    for (int c = 0; c < 6; ++c) g[0][c] = ld_stream2(ge + c * 512 + t_g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) sts2(A + k * AX8_PS + t_s, uc[k]);
     __syncwarp();
@@ -167,16 +186,21 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
     __syncwarp();
 
     // P3: t-derivative in registers, apply G, start D^T in t; wr -> A, ws -> B
+#pragma unroll
+    for (int q = 1; q < GPD; ++q) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) g[q][c] = ld_stream2(ge + c * 512 + q * 64 + t_g);
+    }
     double2 acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = make_double2(0.0, 0.0);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      double2 gn[6];
-      if (k < 7) {
+      if (k + GPD < 8) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) gn[c] = ld_stream2(ge + c * 512 + (k + 1) * 64 + t_g);
+        for (int c = 0; c < 6; ++c) g[(k + GPD) % GS][c] = ld_stream2(ge + c * 512 + (k + GPD) * 64 + t_g);
       }
+      const double2(&gk)[6] = g[k % GS];
       const double2 ur = lds2(A + k * AX8_PS + t_s);
       const double2 us = lds2(B + k * AX8_PS + t_s);
       double2 ut = make_double2(0.0, 0.0);
@@ -186,22 +210,18 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
         ut.y = fma(Dp.d[2][k * 8 + m], uc[m].y, ut.y);
       }
       double2 wr, ws, wt;
-      wr.x = g[0].x * ur.x + g[1].x * us.x + g[2].x * ut.x;
-      wr.y = g[0].y * ur.y + g[1].y * us.y + g[2].y * ut.y;
-      ws.x = g[1].x * ur.x + g[3].x * us.x + g[4].x * ut.x;
-      ws.y = g[1].y * ur.y + g[3].y * us.y + g[4].y * ut.y;
-      wt.x = g[2].x * ur.x + g[4].x * us.x + g[5].x * ut.x;
-      wt.y = g[2].y * ur.y + g[4].y * us.y + g[5].y * ut.y;
+      wr.x = gk[0].x * ur.x + gk[1].x * us.x + gk[2].x * ut.x;
+      wr.y = gk[0].y * ur.y + gk[1].y * us.y + gk[2].y * ut.y;
+      ws.x = gk[1].x * ur.x + gk[3].x * us.x + gk[4].x * ut.x;
+      ws.y = gk[1].y * ur.y + gk[3].y * us.y + gk[4].y * ut.y;
+      wt.x = gk[2].x * ur.x + gk[4].x * us.x + gk[5].x * ut.x;
+      wt.y = gk[2].y * ur.y + gk[4].y * us.y + gk[5].y * ut.y;
       sts2(A + k * AX8_PS + t_s, wr);
       sts2(B + k * AX8_PS + t_s, ws);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         acc[kk].x = fma(Dp.d[2][k * 8 + kk], wt.x, acc[kk].x);
         acc[kk].y = fma(Dp.d[2][k * 8 + kk], wt.y, acc[kk].y);
-      }
-      if (k < 7) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) g[c] = gn[c];
       }
       __syncwarp();  // also keeps the compiler from hoisting every plane's G loads (register blow-up)
     }
@@ -264,7 +284,7 @@ ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) 
         if (mb & 2ull) o.y = 0.0;
       }
       if (DOT) dot = fma(o.x, uc[k].x, fma(o.y, uc[k].y, dot));
-      if (live) *reinterpret_cast<double2*>(we + k * 64 + t_g) = o;
+      if (live) st_out2(we + k * 64 + t_g, o);
     }
   }
   if (DOT) {

@@ -27,6 +27,18 @@
 
 #include "ax_common.cuh"
 
+#ifndef AXL_GPD
+#define AXL_GPD 0  // planes of G in flight ahead of the plane being used; 0 = per-order default (build knob)
+#endif
+// Where the bulk L2 prefetch of the element's G is issued (build knob; -1 = the measured best):
+//   0 first thing (rounds 1-2), 1 behind the loads of P1, 2 after P1, 3 first half of every component behind the
+//   loads of P1 and the second half after the first barrier.
+// The loads of P1 are what the CTA waits for first; queued behind 196 KB of prefetch (Nq = 16) they arrive late.
+// Plain operator, Nq = 16, 16.8 M nodes: 230 (0) -> 218 (1) / 220 (3) us; PCG iteration 479 -> 456 (1) / 448 (3) us.
+#ifndef AX_PF_POS
+#define AX_PF_POS -1
+#endif
+
 namespace semb {
 
 template <int NQ>
@@ -47,6 +59,12 @@ struct AxlCfg {
   static constexpr int BY_REGS = (512 / NT) > 0 ? (512 / NT) : 1;
   static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024) > 0 ? (227 * 1024) / (SMEM + 1024) : 1;
   static constexpr int MINB = BY_REGS < BY_SMEM ? BY_REGS : BY_SMEM;
+  // planes of G requested ahead of the one in use (ring of GPD + 1 register sets).  Measured, plain operator
+  // at ~16 M nodes: Nq = 11: 205 / 198 / 191 / 188 us for 1 / 2 / 3 / 4 planes (4 planes: spills in the CG
+  // variant), Nq = 13: 217 / 205 / 207 / 213, Nq = 16: 231 / 227 / 227 / 227; the low orders are untested: 1.
+  static constexpr int GPD_DEFAULT = NQ >= 13 ? 2 : (NQ >= 9 ? 3 : 1);
+  static constexpr int GPD_WANT = AXL_GPD > 0 ? AXL_GPD : GPD_DEFAULT;
+  static constexpr int GPD = GPD_WANT < NQ - 1 ? GPD_WANT : NQ - 1;
 };
 
 template <int NQ, bool TRANSPOSE>
@@ -124,13 +142,22 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
   const double* ge = a.G6 + e * (int64_t)(6 * NP);
 
   // bulk L2 prefetch of the element's block of G (see ax8_kernel)
-  if (a.l2_prefetch) {
-    if ((NP % 2) == 0) {
-      if (tid < 6) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge + tid * NP), "r"(NP * 8) : "memory");
-    } else if (tid == 0) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge), "r"(6 * NP * 8) : "memory");
+  // half = 0: the whole block; 1 / 2: first / second half of every component (position 3)
+  auto prefetch_g = [&](int half = 0) {
+    if (a.l2_prefetch) {
+      if ((NP % 4) == 0) {
+        const int bytes = half == 0 ? NP * 8 : NP * 4;
+        const double* src = ge + tid * NP + (half == 2 ? NP / 2 : 0);
+        if (tid < 6) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      } else if ((NP % 2) == 0) {
+        if (tid < 6 && half != 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge + tid * NP), "r"(NP * 8) : "memory");
+      } else if (tid == 0 && half != 2) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ge), "r"(6 * NP * 8) : "memory");
+      }
     }
-  }
+  };
+  constexpr int PF = AX_PF_POS >= 0 ? AX_PF_POS : (DIR != 0 ? 3 : 1);
+  if (PF == 0) prefetch_g();
 
   // T layout: column (ti, tj)
   const int ti = tid % NQ, tj = tid / NQ;
@@ -150,23 +177,43 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
     const double* re = a.r + e * NP;
     const double* de = a.dinv + e * NP;
     double* pe = a.p_out + e * NP;
+    double rv[NQ], dv[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
-      const double rv = __ldg(re + k * NL + t_g);
-      const double dv = DIR == 2 ? __ldg(de + k * NL + t_g) : 0.0;
-      uc[k] = dir_update<DIR>(uc[k], rv, dv, beta);
-      if (live) pe[k * NL + t_g] = uc[k];
+      rv[k] = __ldg(re + k * NL + t_g);
+      dv[k] = DIR == 2 ? __ldg(de + k * NL + t_g) : 0.0;
     }
-  }
-  double g[6], gn[6];
+    if (PF == 1) prefetch_g();
+    if (PF == 3) prefetch_g(1);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) g[c] = __ldcs(ge + c * NP + t_g);
+    for (int k = 0; k < NQ; ++k) {
+      uc[k] = dir_update<DIR>(uc[k], rv[k], dv[k], beta);
+      if (live) st_out(pe + k * NL + t_g, uc[k]);
+    }
+  } else if (PF == 1) {
+    prefetch_g();
+  } else if (PF == 3) {
+    prefetch_g(1);
+  }
+  if (PF == 2) prefetch_g();
+  // G runs GPD planes ahead of its use in a ring of GPD + 1 register sets (plane 0 is requested here,
+  // planes 1 .. GPD-1 behind P2 where the registers are free again)
+  constexpr int GPD = AxlCfg<NQ>::GPD, GS = GPD + 1;
+  double g[GS][6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) g[0][c] = __ldcs(ge + c * NP + t_g);
 #pragma unroll
   for (int k = 0; k < NQ; ++k) A[k * PS + t_s] = uc[k];
   __syncthreads();
+  if (PF == 3) prefetch_g(2);
 
   // P2: u_r (A rows -> C rows) and u_s (A columns -> B columns), one shared sweep over D
   line_pair<NQ, false>(Dp.d[0], A + row, Cc + row, A + col, B + col);
+#pragma unroll
+  for (int q = 1; q < GPD; ++q) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) g[q][c] = __ldcs(ge + c * NP + q * NL + t_g);
+  }
   __syncthreads();
 
   // P3: u_t in registers, G, (w_r, w_s, w_t) -> (A, B, C) at the thread's own location; p.Ap
@@ -176,23 +223,20 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
     line_contract<NQ, false>(Dp.d[1], uc, ut);
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
-      if (k < NQ - 1) {
+      if (k + GPD < NQ) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) gn[c] = __ldcs(ge + c * NP + (k + 1) * NL + t_g);
+        for (int c = 0; c < 6; ++c) g[(k + GPD) % GS][c] = __ldcs(ge + c * NP + (k + GPD) * NL + t_g);
       }
+      const double(&gk)[6] = g[k % GS];
       const double ur = Cc[k * PS + t_s];
       const double us = B[k * PS + t_s];
-      const double wr = g[0] * ur + g[1] * us + g[2] * ut[k];
-      const double ws = g[1] * ur + g[3] * us + g[4] * ut[k];
-      const double wt = g[2] * ur + g[4] * us + g[5] * ut[k];
+      const double wr = gk[0] * ur + gk[1] * us + gk[2] * ut[k];
+      const double ws = gk[1] * ur + gk[3] * us + gk[4] * ut[k];
+      const double wt = gk[2] * ur + gk[4] * us + gk[5] * ut[k];
       if (DOT) dot = fma(ur, wr, fma(us, ws, fma(ut[k], wt, dot)));
       A[k * PS + t_s] = wr;
       B[k * PS + t_s] = ws;
       Cc[k * PS + t_s] = wt;
-      if (k < NQ - 1) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) g[c] = gn[c];
-      }
       __syncwarp();  // scheduling fence: keeps the compiler from hoisting every plane's G loads
     }
   }
@@ -230,7 +274,7 @@ axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> D
         o = 0.0;
       }
     }
-    if (live) we[k * NL + t_g] = o;
+    if (live) st_out(we + k * NL + t_g, o);
   }
   if (DOT) {
     const double cta = block_sum_nt<NT>(live ? dot : 0.0);
