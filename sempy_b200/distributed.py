@@ -42,9 +42,20 @@ class TorchComm:
     """torch.distributed as the control-plane communicator (gloo or nccl backend)."""
 
     def __init__(self, group=None):
+        """Collective when the default backend is NCCL and no group is given: every rank must construct it.
+
+        The control plane moves pickled host objects (candidate coordinates, IPC handles).  Over NCCL that
+        is a host -> device -> host round trip and the first collective pays NCCL's lazy connection set-up
+        inside the mesh set-up (0.6-2.5 s of `build_halo` on 2-8 ranks); a gloo group next to the NCCL one
+        keeps it on the host."""
         import torch.distributed as dist
 
         self._dist = dist
+        if group is None and dist.get_backend() == "nccl":
+            try:
+                group = dist.new_group(backend="gloo")
+            except Exception:  # no usable interface for gloo: stay on the default group
+                group = None
         self._group = group
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)

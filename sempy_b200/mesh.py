@@ -211,6 +211,21 @@ class _NodeArray:
         return self.dev().ptr
 
 
+class _TimedComm:
+    """Communicator proxy that adds up the time spent in collectives (set-up breakdown of bench.py)."""
+
+    def __init__(self, comm):
+        self._comm, self.rank, self.size, self.seconds = comm, comm.rank, comm.size, 0.0
+
+    def allgather(self, obj):
+        import time
+
+        t0 = time.perf_counter()
+        out = self._comm.allgather(obj)
+        self.seconds += time.perf_counter() - t0
+        return out
+
+
 class Mesh:
     def __init__(self, fname, debug=0, comm=None):
         if not isinstance(fname, str):
@@ -524,7 +539,9 @@ class Mesh:
                 lead.append(a._dev.to_host(ne * Np).reshape(ne, Np))
         # the union of all ranks' candidates is numbered with the same rule -- on the device when set-up runs there
         number = global_numbering_device if device_setup_enabled() else global_numbering_from_coordinates
-        self._halo = distributed.build_halo(self.comm, lead[0], lead[1], lead[2], cand, lead[3], number)
+        timed = _TimedComm(self.comm)
+        self._halo = distributed.build_halo(timed, lead[0], lead[1], lead[2], cand, lead[3], number)
+        self.halo_timings = dict(self.halo_timings, build_halo_allgather=round(timed.seconds, 3))
 
     def setup_mask(self):
         """Homogeneous Dirichlet mask of the bounding box (sempy/mesh.py:449-477); with several ranks the box
@@ -618,7 +635,7 @@ class Mesh:
             mark("p2p_alloc_allgather")
             _capi.check(lib.semb_p2p_attach(ctx.handle, blob, peer_off.ctypes.data))
             mark("p2p_attach")
-        self.halo_timings = marks
+        self.halo_timings = dict(self.halo_timings, **marks)
 
     def _vector_args(self, x, name):
         """(pointer, mem flag, keep-alive) for an in-place vector argument."""
