@@ -33,6 +33,7 @@ struct AxArgs {
   int ncta_total;    // DOT: CTAs of the logical grid (several launches may share it)
   int64_t e0, e1;    // element range of this launch
   int l2_prefetch;
+  int pdl;           // host side only: launch with the programmatic-stream-serialization attribute
 };
 
 __device__ __forceinline__ double2 ld_stream2(const double* p) {

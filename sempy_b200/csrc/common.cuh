@@ -56,6 +56,46 @@ const NcclApi& nccl();  // loads on first use; ok == false if no NCCL library co
     }                                                                                        \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// Inside semb_cg on one GPU the three kernels of an iteration depend on each other only through "the previous
+// grid has completed".  Launched with the programmatic-stream-serialization attribute, a kernel may become
+// resident while its predecessor drains: every kernel of the chain first lets ITS dependents be scheduled
+// (pdl_launch_dependents) and then waits until the predecessor has completed and its writes are visible
+// (pdl_wait) before it reads anything the predecessor produced -- including the `done` flag.  Launch latency
+// and the ramp-up of the next grid overlap the tail of the previous one.  Both instructions are no-ops in a
+// kernel that was launched normally.
+#ifdef __CUDACC__
+// SEMB_PDL_EARLY = 1 lets the dependents become resident as soon as every CTA of this grid has started.  Measured:
+// the waiting CTAs of the NEXT grids (the operator kernel's need 128 registers x 128 threads and 45 KB each) take the
+// slots the running grid's later CTAs need: 416 -> 494 us per PCG iteration at 32^3 N=7.  Off: dependents are
+// released when this grid's CTAs exit (only the launch latency is hidden).
+#ifndef SEMB_PDL_EARLY
+#define SEMB_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if SEMB_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 #define SEMB_CHECK(cond, msg)              \
   do {                                     \
     if (!(cond)) {                         \

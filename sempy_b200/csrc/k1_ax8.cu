@@ -63,6 +63,8 @@ __device__ __forceinline__ void line8x2(const double (&D)[64], const double (&a)
 template <bool MASK, bool DOT, int DIR>
 __global__ void __launch_bounds__(AX8_WARPS * 32, 16 / AX8_WARPS)
 ax8_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMat8x Dp) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,8 +312,8 @@ static int launch_ax8_t(const AxArgs& a, const DMat8x& d8, cudaStream_t st, int 
     SEMB_CUDA(cudaFuncSetAttribute(ax8_kernel<MASK, DOT, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done[device & 63] = true;
   }
-  ax8_kernel<MASK, DOT, DIR><<<(unsigned)ax8_num_ctas(a.e0, a.e1), AX8_WARPS * 32, AX8_SMEM, st>>>(a, d8);
-  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(launch_maybe_pdl(ax8_kernel<MASK, DOT, DIR>, dim3((unsigned)ax8_num_ctas(a.e0, a.e1)), dim3(AX8_WARPS * 32), AX8_SMEM, st,
+                             a.pdl != 0, a, d8));
   return 0;
 }
 

@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(AxlCfg<NQ>::NT, AxlCfg<NQ>::MINB)
 axl_kernel(const __grid_constant__ AxArgs a, const __grid_constant__ DMatL<NQ> Dp) {
   using C = AxlCfg<NQ>;
   constexpr int NT = C::NT, NL = NQ * NQ, NP = NQ * NQ * NQ, RS = C::RS, PS = C::PS;
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) double smem[];
   const int el = C::EPB > 1 ? (int)threadIdx.x / NL : 0;      // element slot of this thread inside the CTA
@@ -292,8 +294,8 @@ static int launch_axl_t(const AxArgs& a, const DMatL<NQ>& dl, cudaStream_t st, i
     SEMB_CUDA(cudaFuncSetAttribute(axl_kernel<NQ, MASK, DOT, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done[device & 63] = true;
   }
-  axl_kernel<NQ, MASK, DOT, DIR><<<(unsigned)((a.e1 - a.e0 + Cfg::EPB - 1) / Cfg::EPB), Cfg::NT, Cfg::SMEM, st>>>(a, dl);
-  SEMB_CUDA(cudaGetLastError());
+  SEMB_CUDA(launch_maybe_pdl(axl_kernel<NQ, MASK, DOT, DIR>, dim3((unsigned)((a.e1 - a.e0 + Cfg::EPB - 1) / Cfg::EPB)), dim3(Cfg::NT),
+                             Cfg::SMEM, st, a.pdl != 0, a, dl));
   return 0;
 }
 

@@ -33,6 +33,8 @@ static int g_ax_l2_prefetch = env_int("SEMB_AX_L2_PREFETCH", 1);
 // "gs_pull": 0 = the whole gather-scatter as a separate in-place pass (push form) instead of summing the
 // two-copy segments inside the consumer (CG update kernel)
 static int g_gs_pull = env_int("SEMB_GS_PULL", 1);
+// "pdl": 1 = the kernels of a CG iteration on one GPU are chained by programmatic dependent launch (common.cuh)
+static int g_pdl = env_int("SEMB_PDL", 1);
 
 const NcclApi& nccl() {
   static NcclApi api = [] {
@@ -125,7 +127,7 @@ static void drop_jacobi(semb_ctx* c) {
 // p_out (dir != 0): where the updated direction goes (nullptr: in place)
 static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool dot, int dir, int64_t e0, int64_t e1,
                      const double* r, const double* dinv, int cta_off, int ncta_total, const int* done,
-                     cudaStream_t st = nullptr, bool prof = true, double* p_out = nullptr) {
+                     cudaStream_t st = nullptr, bool prof = true, double* p_out = nullptr, bool pdl = false) {
   if (e1 <= e0) return 0;
   if (st == nullptr) st = c->stream;
   ProfScope ps(prof ? c : nullptr, SEMB_K_AX, st);
@@ -146,6 +148,7 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
   a.e0 = e0;
   a.e1 = e1;
   a.l2_prefetch = g_ax_l2_prefetch;
+  a.pdl = pdl ? 1 : 0;
   if (c->Nq == 8) return launch_ax8(a, c->D, mask, dot, dir, st, c->device);
   if (c->Nq >= 3) return launch_axl(c->Nq, a, c->D, mask, dot, dir, st, c->device);
   return launch_ax_generic(c->Nq, a, c->D, mask, dot, dir, st);
@@ -157,7 +160,8 @@ static int launch_ax(semb_ctx* c, const double* p, double* ap, bool mask, bool d
 // (compact form, c->gs_sums), nothing is written back to x (pull form, gs_linked)
 // pass_n > 0: the pass_n partial sums of p.Ap in c->partials are added up (fixed order) into *pass_out by a
 // passenger CTA of the gather-scatter launch, or by a launch of their own when there is nothing to gather
-static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false, int pass_n = 0, double* pass_out = nullptr) {
+static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false, int pass_n = 0, double* pass_out = nullptr,
+                     bool pdl = false) {
   const bool skip_pairs = pull;
   double* sums = pull ? c->gs_sums : nullptr;
   ProfScope ps(c, SEMB_K_GS);
@@ -181,9 +185,8 @@ static int launch_gs(semb_ctx* c, double* x, const int* done, bool pull = false,
     c->launch_count++;
     GsPassenger pass{pass_n > 0 ? c->partials : nullptr, pass_n, pass_out,
                      GridRed{c->pass_part, c->pass_part + 32, c->pass_tick}};
-    gs_fixed_kernel<<<total_blocks + (pass_n > 0 ? GS_PASSENGERS : 0), VEC_NT, 0, c->stream>>>(x, c->gs_ids, plan, done, sums,
-                                                                                            pass);
-    SEMB_CUDA(cudaGetLastError());
+    SEMB_CUDA(launch_maybe_pdl(gs_fixed_kernel, dim3(total_blocks + (pass_n > 0 ? GS_PASSENGERS : 0)), dim3(VEC_NT), 0, c->stream, pdl,
+                               x, c->gs_ids, plan, done, sums, pass));
   } else if (pass_n > 0) {
     c->launch_count++;
     reduce_partials_kernel<<<1, RED_NT, 0, c->stream>>>(c->partials, pass_n, 0, 1, pass_out, done);
@@ -1397,6 +1400,8 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
   const bool multi = c->nranks > 1;
   const bool p2p = multi && use_p2p(c);
   const bool pull = use_pull(c);
+  // programmatic dependent launch along K1 -> K2' -> K3 -> K1 ...: one GPU, no FDM launch in between
+  const bool pdl = g_pdl != 0 && !multi && !fdm;
 
   // x = 0, r = b, p = 0; |b|_w^2 and r.z                          (elliptic.py:31-46, iterative.py:48-63)
   c->launch_count += 2;
@@ -1478,8 +1483,8 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         SEMB_TRY(allreduce_sum(c, &s->pAp, 1));
         SEMB_TRY(halo_scatter(c, Ap, c->stream, done));
       } else {
-        SEMB_TRY(launch_ax(c, p_old, Ap, mask, true, dir, 0, c->E, zsrc, dinv, 0, cta2, done, nullptr, true, p));
-        SEMB_TRY(launch_gs(c, Ap, done, pull, npart, &s->pAp));
+        SEMB_TRY(launch_ax(c, p_old, Ap, mask, true, dir, 0, c->E, zsrc, dinv, 0, cta2, done, nullptr, true, p, pdl));
+        SEMB_TRY(launch_gs(c, Ap, done, pull, npart, &s->pAp, pdl));
       }
       // x += alpha p (every second iteration, two terms at once); r -= alpha dssum(Ap); r.z; scalar step
       // (elliptic.py:56-71)
@@ -1493,9 +1498,9 @@ int semb_cg(semb_ctx* c, const double* b, double* x, double tol, int maxit, int 
         LlArgs ll = ll_args(c, 0);
         ll.nranks = 1;
         if (tail && p2p) ll = ll_args(c, ++c->seq_scalar);
-#define SEMB_UPDATE_X(J, P, X)                                                                                         \
-  cg_update_kernel<J, P, X><<<grid, VEC_NT, 0, c->stream>>>(xdev, r, p, p_old, Ap, c->mult, dinv, c->gs_link, c->gs_sums, \
-                                                           s, n, c->partials, ticket, hist, ll)
+#define SEMB_UPDATE_X(J, P, X)                                                                                        \
+  SEMB_CUDA(launch_maybe_pdl(cg_update_kernel<J, P, X>, dim3(grid), dim3(VEC_NT), 0, c->stream, pdl, xdev, r, p, p_old, Ap, \
+                             c->mult, dinv, c->gs_link, c->gs_sums, s, n, c->partials, ticket, hist, ll))
 #define SEMB_UPDATE(J, P)                  \
   do {                                     \
     if (k & 1) SEMB_UPDATE_X(J, P, 2);     \
@@ -1851,6 +1856,10 @@ int semb_set_tuning(const char* name, int value) {
   }
   if (std::strcmp(name, "gs_pull") == 0) {
     g_gs_pull = value;
+    return 0;
+  }
+  if (std::strcmp(name, "pdl") == 0) {
+    g_pdl = value;
     return 0;
   }
   if (std::strcmp(name, "p2p") == 0) {

@@ -132,6 +132,8 @@ __device__ __forceinline__ void gs_passenger(const GsPassenger& pass, int slice)
 __global__ void __launch_bounds__(VEC_NT)
 gs_fixed_kernel(double* __restrict__ x, const int32_t* __restrict__ ids, const GsPlan plan,
                 const int* __restrict__ done, double* __restrict__ sums, const GsPassenger pass) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (done != nullptr && *done) return;
   int b = blockIdx.x;
   if (pass.part != nullptr) {
@@ -580,6 +582,8 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* _
                  const uint32_t* __restrict__ link, const double* __restrict__ sums, CgScalars* __restrict__ s, int64_t n,
                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ hist,
                  const LlArgs ll) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (s->done) return;
   __shared__ double s_rcp[256];
   s_rcp[threadIdx.x] = 1.0 / (double)(threadIdx.x > 0 ? threadIdx.x : 1);  // VEC_NT == 256 entries
