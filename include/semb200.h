@@ -253,7 +253,8 @@ int64_t semb_launch_count(semb_ctx* ctx);
  * vs NCCL for the halo exchange and the scalar all-reduces.  "gs_pull": 1 (default) / 0,
  * inside semb_cg the two-copy segments of the gather-scatter are summed by the CG
  * update kernel while it streams (only the longer segments keep an in-place pass)
- * vs one in-place pass over all segments. */
+ * vs one in-place pass over all segments.  "pdl": 1 (default) / 0, the kernels of
+ * a CG iteration on one GPU are chained by programmatic dependent launch. */
 int semb_set_tuning(const char* name, int value);
 
 #ifdef __cplusplus
