@@ -380,7 +380,8 @@ def test_full_size_properties(big_mesh):
 def test_bitwise_repeatable_and_independent_of_the_gs_form():
     """Every sum of the solver has a fixed order (no floating-point atomics): two solves give the same
     bits, and so does the solve with the pairwise gather-scatter as a separate in-place pass
-    (gs_pull = 0) instead of inside the update kernel (a + b commutes exactly)."""
+    (gs_pull = 0) instead of inside the update kernel (a + b commutes exactly), and the solve whose kernels are
+    launched one after the other (pdl = 0) instead of chained by programmatic dependent launch."""
     from sempy_b200 import _capi
     from sempy_b200.elliptic import elliptic_cg, elliptic_pcg
     from sempy_b200.mesh import box_mesh
@@ -394,10 +395,15 @@ def test_bitwise_repeatable_and_independent_of_the_gs_form():
     b = m.apply_mask(m.dssum(rng.standard_normal(m.get_num_elems() * m.Np)))
     lib = _capi.lib()
     runs = []
-    for pull in (1, 1, 0):
-        _capi.check(lib.semb_set_tuning(b"gs_pull", pull))
-        runs.append((elliptic_pcg(m, b, tol=1e-10, maxit=500), elliptic_cg(m, b, tol=1e-9, maxit=40)))
-    _capi.check(lib.semb_set_tuning(b"gs_pull", 1))
+    try:
+        # (gs_pull, pdl): the default twice, the in-place gather-scatter, plain instead of programmatic launches
+        for pull, pdl in ((1, 1), (1, 1), (0, 1), (1, 0)):
+            _capi.check(lib.semb_set_tuning(b"gs_pull", pull))
+            _capi.check(lib.semb_set_tuning(b"pdl", pdl))
+            runs.append((elliptic_pcg(m, b, tol=1e-10, maxit=500), elliptic_cg(m, b, tol=1e-9, maxit=40)))
+    finally:
+        _capi.check(lib.semb_set_tuning(b"gs_pull", 1))
+        _capi.check(lib.semb_set_tuning(b"pdl", 1))
     for (xp, itp), (xc, itc) in runs[1:]:
         assert itp == runs[0][0][1] and itc == runs[0][1][1]
         assert np.array_equal(xp, runs[0][0][0]) and np.array_equal(xc, runs[0][1][0])
