@@ -7,7 +7,8 @@
 //   S: thread (i, k) owns the s-line (stride = one padded row)
 // The element lives in shared memory as THREE staged arrays of Nq planes (110 KB at Nq = 16, two CTAs =
 // 16 warps per SM -- the "shared-memory pressure" of BASELINE config 3):
-//   P1  u -> registers (T columns) and A                                  (+ the folded direction update)
+//   P1  u -> registers (T columns) and A   (+ the folded direction update); requests enter the memory system in the
+//       order they are needed: the loads of P1, then the bulk L2 prefetch of G (AX_PF_POS below)
 //   P2  r-line of A -> C (u_r) and s-line of A -> B (u_s) in ONE pass: both lines use the same entry of D
 //       for the same output index, so every D operand fetched (LDCU -> uniform register) feeds two DFMAs
 //   P3  u_t = D_t u in registers; per plane: G, (w_r, w_s, w_t) -> (A, B, C) at the thread's own T location;
