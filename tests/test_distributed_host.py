@@ -124,3 +124,18 @@ def test_non_planar_interfaces(size, dims, perturb, N, tmp_path):
     assert res.shape[0] == size
     assert res[:, 0].max() < 1e-15 and res[:, 1].all() and res[:, 2].all() and res[:, 3].all()
     assert (res[:, 4] > 0).all()
+
+
+def test_first_occurrence_by_reversed_assignment():
+    """build_halo finds the first send entry of every interface node with a fancy assignment written back to
+    front (the smallest index wins because NumPy keeps the last value assigned to a repeated index); pinned
+    here against np.minimum.at so that a change of that behaviour is noticed."""
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n_if, n_send = int(rng.integers(1, 60)), int(rng.integers(1, 300))
+        node_of = rng.integers(0, n_if, n_send)
+        want = np.full(n_if, n_send, dtype=np.int64)
+        np.minimum.at(want, node_of, np.arange(n_send))
+        got = np.full(n_if, n_send, dtype=np.int64)
+        got[node_of[::-1]] = np.arange(n_send - 1, -1, -1)
+        assert np.array_equal(got, want)
