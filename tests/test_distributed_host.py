@@ -52,14 +52,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, size, port, dims, perturb, N, out):
+def _worker(rank, size, port, dims, perturb, N, out, side_group=False):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
+        if side_group:
+            # as under torchrun with the NCCL backend: the control plane must move to a gloo group of its own
+            dist.get_backend = lambda *a, **k: "nccl"
         comm = dd.TorchComm()
+        assert (comm._group is not None) == side_group
         pts, hexes = pm.box_mesh_arrays(*dims, perturb=perturb, seed=2)
         m = pm.Mesh.from_arrays(pts, hexes, comm=comm)
         # coordinates from the oracle (the product computes them on the GPU); numbering rule is the product's
@@ -110,6 +114,17 @@ def test_halo_tables_reproduce_global_gather_scatter(size, dims, perturb, N, tmp
     expect_if = [plane * (1 if r in (0, size - 1) else 2) for r in range(size)]
     assert list(res[:, 4].astype(int)) == expect_if
     assert list(res[:, 5].astype(int)) == [1 if r in (0, size - 1) else 2 for r in range(size)]
+
+
+def test_control_plane_on_a_side_group(tmp_path):
+    """With NCCL as the default backend TorchComm opens a gloo group for its pickled host objects (no
+    host -> device -> host round trip, no NCCL connection set-up inside the mesh set-up); same tables."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, _free_port(), (2, 3, 4), 0.2, 3, out, True), nprocs=2, join=True)
+    res = np.load(out)
+    assert res[:, 0].max() < 1e-15 and res[:, 1].all() and res[:, 2].all() and res[:, 3].all()
 
 
 @pytest.mark.parametrize("size,dims,perturb,N", [(2, (3, 3, 3), 0.3, 3), (3, (2, 2, 5), 0.2, 2), (4, (3, 3, 3), 0.0, 2)])
